@@ -1,0 +1,138 @@
+/*
+ * jwave_cuda.h - C ABI of libjwave_cuda.so, the B200 (sm_100a) implementation of JWave's
+ * discrete-wavelet hot path.
+ *
+ * This is the drop-in boundary: the entry points below are exactly what a JWave-side FFI
+ * binding (Java 21 java.lang.foreign, see INTEGRATION.md and java/) needs in order to put the
+ * GPU behind `BasicTransform` subclasses while `Transform.forward/reverse` stays unchanged.
+ * Plain pointers and sizes only; no C++ or torch types.  Every function that returns `int`
+ * returns a jwc_status (0 = OK).
+ *
+ * Reference interfaces replaced (paths relative to /root/reference/src/main/java/jwave/):
+ *   Wavelet.forward / Wavelet.reverse              transforms/wavelets/Wavelet.java:236-260, :277-303
+ *   FastWaveletTransform.forward / reverse         transforms/FastWaveletTransform.java:71-101, :119-153
+ *   WaveletPacketTransform.forward / reverse       transforms/WaveletPacketTransform.java:73-124, :141-191
+ *   (Pooled|Parallel)WaveletPacketTransform        transforms/PooledWaveletPacketTransform.java:24-127,
+ *                                                  transforms/ParallelWaveletPacketTransform.java:79-146
+ *   BasicTransform 2-D forward / reverse           transforms/BasicTransform.java:361-399, :436-474
+ *   BasicTransform 3-D forward / reverse           transforms/BasicTransform.java:509-566, :602-659
+ *
+ * Data layout: every array is dense, row-major, contiguous IEEE binary64.  A batch of 1-D
+ * signals is [batch][n]; a batch of matrices is [batch][rows][cols]; a volume is [P][Q][R]
+ * indexed [i][j][k] like Java's double[P][Q][R].
+ *
+ * Semantics are the reference's: periodic extension to the right, outputs laid out as
+ * [a_l | d_l | ... | d_1] (FWT) or as 2^l packets in natural order (WPT); inputs are never
+ * modified; `level` counts decomposition steps, 0 <= level <= log2(n).
+ *
+ * There is no CPU fallback: every entry point either runs the CUDA kernels or fails.
+ */
+#ifndef JWAVE_CUDA_H
+#define JWAVE_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JWC_VERSION 100 /* 0.1.0 */
+#define JWC_MAX_TAPS 40 /* Daubechies20 / Symlet20 */
+
+typedef struct jwc_ctx jwc_ctx;
+
+typedef enum jwc_status {
+  JWC_OK = 0,
+  JWC_ERR_NOT_BINARY = 1, /* a length is not 2^p      -> JWaveFailure (FastWaveletTransform.java:74-78) */
+  JWC_ERR_LEVEL = 2,      /* level outside [0, log2 n] -> JWaveFailure (FastWaveletTransform.java:81-83) */
+  JWC_ERR_ARG = 3,        /* null pointer, bad handle, odd filter length, aliasing, ... */
+  JWC_ERR_CUDA = 4,       /* a CUDA runtime call failed; see jwc_last_error */
+  JWC_ERR_NCCL = 5        /* reserved: the exchange step of the slab-decomposed 3-D path */
+} jwc_status;
+
+enum { JWC_FORWARD = 0, JWC_REVERSE = 1 };
+enum { JWC_FWT = 0, JWC_WPT = 1 };
+
+int jwc_version(void);
+
+/* One context = one GPU + one stream.  `device` is a CUDA ordinal.  A context serialises the
+ * calls made on it; use one context per host thread (the reference's transforms are stateless,
+ * BasicTransform.java:42). */
+int jwc_create(jwc_ctx** out, int device);
+int jwc_destroy(jwc_ctx* ctx);
+/* Text of the last failure on this context (never NULL). With ctx == NULL: creation failures. */
+const char* jwc_last_error(const jwc_ctx* ctx);
+
+/* Launch on a caller-owned cudaStream_t (e.g. torch's current stream) instead of the context's
+ * own.  Pass NULL to go back to the context's stream. */
+int jwc_set_stream(jwc_ctx* ctx, void* cuda_stream);
+int jwc_sync(jwc_ctx* ctx);
+/* Number of kernels this context has launched so far. */
+int64_t jwc_launch_count(const jwc_ctx* ctx);
+
+/* Register a wavelet from the four arrays returned by the reference's getters
+ * (Wavelet.getScalingDeComposition() ... getWaveletReConstruction(), Wavelet.java:178-219), so
+ * the device filters are bit-identical to the JVM's.  L must be even, 2 <= L <= JWC_MAX_TAPS.
+ * The taps travel to the kernels as a __grid_constant__ parameter, i.e. in constant memory.
+ * On success *wid is a handle valid until the context is destroyed. */
+int jwc_set_wavelet(jwc_ctx* ctx, int L, const double* scalingDeCom, const double* waveletDeCom,
+                    const double* scalingReCon, const double* waveletReCon, int* wid);
+
+/* ---- host-buffer entry points: H2D copy, kernels, D2H copy, synchronous on return ---------- */
+
+/* FastWaveletTransform.forward/reverse(double[], int) over `batch` signals of length n. */
+int jwc_fwt1d(jwc_ctx* ctx, int wid, int dir, const double* in, double* out, int64_t batch, int n,
+              int level);
+/* WaveletPacketTransform.forward/reverse(double[], int) over `batch` signals of length n. */
+int jwc_wpt1d(jwc_ctx* ctx, int wid, int dir, const double* in, double* out, int64_t batch, int n,
+              int level);
+/* BasicTransform.forward/reverse(double[][], lvlM, lvlN) with an FWT / a WPT as the 1-D step:
+ * forward = every row with lvlN then every column with lvlM; reverse = columns then rows. */
+int jwc_fwt2d(jwc_ctx* ctx, int wid, int dir, const double* in, double* out, int64_t batch, int rows,
+              int cols, int lvlM, int lvlN);
+int jwc_wpt2d(jwc_ctx* ctx, int wid, int dir, const double* in, double* out, int64_t batch, int rows,
+              int cols, int lvlM, int lvlN);
+/* BasicTransform.forward/reverse(double[][][], lvlP, lvlQ, lvlR), including the reference's
+ * level shift: axis k (length R) gets lvlQ, axis j (length Q) gets lvlP, axis i (length P)
+ * gets lvlR (BasicTransform.java:532, :555). */
+int jwc_fwt3d(jwc_ctx* ctx, int wid, int dir, const double* in, double* out, int P, int Q, int R,
+              int lvlP, int lvlQ, int lvlR);
+int jwc_wpt3d(jwc_ctx* ctx, int wid, int dir, const double* in, double* out, int P, int Q, int R,
+              int lvlP, int lvlQ, int lvlR);
+
+/* ---- device-resident entry points: `in`/`out` are device pointers on the context's GPU,
+ *      must not overlap, and the work is enqueued on the context's stream (no sync) ---------- */
+
+int jwc_fwt1d_dev(jwc_ctx* ctx, int wid, int dir, const double* in, double* out, int64_t batch, int n,
+                  int level);
+int jwc_wpt1d_dev(jwc_ctx* ctx, int wid, int dir, const double* in, double* out, int64_t batch, int n,
+                  int level);
+int jwc_fwt2d_dev(jwc_ctx* ctx, int wid, int dir, const double* in, double* out, int64_t batch,
+                  int rows, int cols, int lvlM, int lvlN);
+int jwc_wpt2d_dev(jwc_ctx* ctx, int wid, int dir, const double* in, double* out, int64_t batch,
+                  int rows, int cols, int lvlM, int lvlN);
+int jwc_fwt3d_dev(jwc_ctx* ctx, int wid, int dir, const double* in, double* out, int P, int Q, int R,
+                  int lvlP, int lvlQ, int lvlR);
+int jwc_wpt3d_dev(jwc_ctx* ctx, int wid, int dir, const double* in, double* out, int P, int Q, int R,
+                  int lvlP, int lvlQ, int lvlR);
+/* The building block the 2-D/3-D drivers and the slab-decomposed multi-GPU volume are made of:
+ * a dense [outer][n][inner] array, 1-D transform (kind = JWC_FWT | JWC_WPT) along the middle
+ * axis of every (outer, inner) line. */
+int jwc_axis_dev(jwc_ctx* ctx, int wid, int kind, int dir, const double* in, double* out,
+                 int64_t outer, int n, int64_t inner, int level);
+
+/* ---- memory helpers for FFI callers ------------------------------------------------------- */
+int jwc_dev_alloc(jwc_ctx* ctx, size_t bytes, void** dptr);
+int jwc_dev_free(jwc_ctx* ctx, void* dptr);
+int jwc_h2d(jwc_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes); /* async on the stream */
+int jwc_d2h(jwc_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes); /* async on the stream */
+int jwc_host_alloc_pinned(jwc_ctx* ctx, size_t bytes, void** hptr);
+int jwc_host_free_pinned(jwc_ctx* ctx, void* hptr);
+/* Upper bound (bytes) for the staging chunk the host-buffer entry points move per step. */
+int jwc_set_staging_bytes(jwc_ctx* ctx, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JWAVE_CUDA_H */

@@ -1,0 +1,479 @@
+// jwc_capi.cu - the C ABI of libjwave_cuda.so (include/jwave_cuda.h): contexts, wavelet
+// registration, argument checks with the reference's failure classes, the host-buffer
+// staging pipeline, and the 2-D / 3-D drivers expressed as axis passes.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "jwc_internal.cuh"
+#include "jwc_plan.cuh"
+
+using namespace jwc;
+
+static std::string g_create_err;
+static std::mutex g_create_mu;
+
+#define JWC_CUDA(ctx, call)                                                              \
+  do {                                                                                   \
+    cudaError_t e__ = (call);                                                            \
+    if (e__ != cudaSuccess) {                                                            \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                  \
+      return JWC_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+
+static int fail(jwc_ctx* ctx, int status, const char* msg) {
+  if (ctx) ctx->err = msg;
+  return status;
+}
+
+extern "C" int jwc_version(void) { return JWC_VERSION; }
+
+extern "C" int jwc_create(jwc_ctx** out, int device) {
+  if (!out) return JWC_ERR_ARG;
+  *out = nullptr;
+  auto bail = [&](const char* what, cudaError_t e) {
+    std::lock_guard<std::mutex> lk(g_create_mu);
+    g_create_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return int(JWC_ERR_CUDA);
+  };
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess) return bail("cudaGetDeviceCount", e);
+  if (device < 0 || device >= count) {
+    std::lock_guard<std::mutex> lk(g_create_mu);
+    g_create_err = "jwc_create: no such CUDA device";
+    return JWC_ERR_ARG;
+  }
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+  jwc_ctx* ctx = new jwc_ctx();
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+    delete ctx;
+    return bail("cudaGetDeviceProperties", e);
+  }
+  if (prop.major < 10) {
+    delete ctx;
+    std::lock_guard<std::mutex> lk(g_create_mu);
+    g_create_err = "jwc_create: libjwave_cuda.so is built for sm_100a (B200) only";
+    return JWC_ERR_CUDA;
+  }
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    delete ctx;
+    return bail("cudaStreamCreate", e);
+  }
+  for (int i = 0; i < 2; ++i) {
+    cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming);
+  }
+  ctx->stream = ctx->own_stream;
+  const char* fg = getenv("JWC_FORCE_GENERIC");
+  ctx->force_generic = fg && fg[0] == '1';
+  *out = ctx;
+  return JWC_OK;
+}
+
+static void free_scratch(Scratch& s) {
+  if (s.ptr) cudaFree(s.ptr);
+  s.ptr = nullptr;
+  s.bytes = 0;
+}
+
+extern "C" int jwc_destroy(jwc_ctx* ctx) {
+  if (!ctx) return JWC_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (auto& s : ctx->scratch) free_scratch(s);
+  for (int i = 0; i < 2; ++i) {
+    free_scratch(ctx->stage_in[i]);
+    free_scratch(ctx->stage_out[i]);
+    if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
+    if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
+    if (ctx->ev_out[i]) cudaEventDestroy(ctx->ev_out[i]);
+  }
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+  if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
+  delete ctx;
+  return JWC_OK;
+}
+
+extern "C" const char* jwc_last_error(const jwc_ctx* ctx) {
+  if (ctx) return ctx->err.c_str();
+  std::lock_guard<std::mutex> lk(g_create_mu);
+  static thread_local std::string copy;
+  copy = g_create_err;
+  return copy.c_str();
+}
+
+extern "C" int jwc_set_stream(jwc_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return JWC_ERR_ARG;
+  ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+  return JWC_OK;
+}
+
+extern "C" int jwc_sync(jwc_ctx* ctx) {
+  if (!ctx) return JWC_ERR_ARG;
+  JWC_CUDA(ctx, cudaSetDevice(ctx->device));
+  JWC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return JWC_OK;
+}
+
+extern "C" int64_t jwc_launch_count(const jwc_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+extern "C" int jwc_set_wavelet(jwc_ctx* ctx, int L, const double* sDe, const double* wDe,
+                               const double* sRe, const double* wRe, int* wid) {
+  if (!ctx) return JWC_ERR_ARG;
+  if (!sDe || !wDe || !sRe || !wRe || !wid) return fail(ctx, JWC_ERR_ARG, "jwc_set_wavelet: null argument");
+  if (L < 2 || L > JWC_MAX_TAPS || (L & 1))
+    return fail(ctx, JWC_ERR_ARG, "jwc_set_wavelet: filter length must be even and within 2..40");
+  WaveletRec rec;
+  memset(&rec, 0, sizeof(rec));
+  rec.L = L;
+  for (int j = 0; j < L; ++j) {
+    rec.de.lo[j] = sDe[j];
+    rec.de.hi[j] = wDe[j];
+    rec.re.lo[j] = sRe[j];
+    rec.re.hi[j] = wRe[j];
+  }
+  ctx->wavelets.push_back(rec);
+  *wid = int(ctx->wavelets.size()) - 1;
+  return JWC_OK;
+}
+
+// ---- argument checks with the reference's failure classes --------------------------------------
+
+static bool is_binary(int64_t v) { return v > 0 && (v & (v - 1)) == 0; }  // MathToolKit.java:185-189
+static int exponent(int64_t v) {                                          // MathToolKit.java:202-208 (F14)
+  int p = 0;
+  while ((int64_t(1) << (p + 1)) <= v) ++p;
+  return p;
+}
+
+static int check_axis(jwc_ctx* ctx, int n, int level) {
+  if (!is_binary(n)) return fail(ctx, JWC_ERR_NOT_BINARY, "given array length is not 2^p | p E N");
+  if (level < 0 || level > exponent(n)) return fail(ctx, JWC_ERR_LEVEL, "given level is out of range for given array");
+  return JWC_OK;
+}
+
+static int check_common(jwc_ctx* ctx, int wid, int kind, int dir, const void* in, const void* out) {
+  if (!ctx) return JWC_ERR_ARG;
+  if (wid < 0 || wid >= int(ctx->wavelets.size())) return fail(ctx, JWC_ERR_ARG, "unknown wavelet handle");
+  if (kind != JWC_FWT && kind != JWC_WPT) return fail(ctx, JWC_ERR_ARG, "kind must be JWC_FWT or JWC_WPT");
+  if (dir != JWC_FORWARD && dir != JWC_REVERSE) return fail(ctx, JWC_ERR_ARG, "dir must be JWC_FORWARD or JWC_REVERSE");
+  if (!in || !out) return fail(ctx, JWC_ERR_ARG, "null data pointer");
+  return JWC_OK;
+}
+
+static bool overlaps(const double* a, const double* b, int64_t count) {
+  return a < b + count && b < a + count;
+}
+
+// ---- device-resident drivers --------------------------------------------------------------------
+
+static int axis_dev(jwc_ctx* ctx, int wid, int kind, int dir, const double* in, double* out,
+                    int64_t outer, int n, int64_t inner, int level) {
+  int st = check_axis(ctx, n, level);
+  if (st) return st;
+  if (outer < 0 || inner < 1) return fail(ctx, JWC_ERR_ARG, "negative batch");
+  if (outer == 0) return JWC_OK;
+  if (overlaps(in, out, outer * n * inner)) return fail(ctx, JWC_ERR_ARG, "in and out overlap");
+  JWC_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaError_t e = run_axis(ctx, ctx->wavelets[wid], kind, dir, in, out, outer, n, inner, level);
+  if (e != cudaSuccess) {
+    ctx->err = std::string("axis transform: ") + cudaGetErrorString(e);
+    return JWC_ERR_CUDA;
+  }
+  return JWC_OK;
+}
+
+extern "C" int jwc_axis_dev(jwc_ctx* ctx, int wid, int kind, int dir, const double* in, double* out,
+                            int64_t outer, int n, int64_t inner, int level) {
+  int st = check_common(ctx, wid, kind, dir, in, out);
+  if (st) return st;
+  return axis_dev(ctx, wid, kind, dir, in, out, outer, n, inner, level);
+}
+
+static int t1d_dev(jwc_ctx* ctx, int wid, int kind, int dir, const double* in, double* out,
+                   int64_t batch, int n, int level) {
+  int st = check_common(ctx, wid, kind, dir, in, out);
+  if (st) return st;
+  return axis_dev(ctx, wid, kind, dir, in, out, batch, n, 1, level);
+}
+
+extern "C" int jwc_fwt1d_dev(jwc_ctx* ctx, int wid, int dir, const double* in, double* out,
+                             int64_t batch, int n, int level) {
+  return t1d_dev(ctx, wid, JWC_FWT, dir, in, out, batch, n, level);
+}
+extern "C" int jwc_wpt1d_dev(jwc_ctx* ctx, int wid, int dir, const double* in, double* out,
+                             int64_t batch, int n, int level) {
+  return t1d_dev(ctx, wid, JWC_WPT, dir, in, out, batch, n, level);
+}
+
+static int ensure(jwc_ctx* ctx, Scratch& s, size_t bytes) {
+  if (s.bytes >= bytes) return JWC_OK;
+  if (s.ptr) {
+    JWC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    JWC_CUDA(ctx, cudaFree(s.ptr));
+    s.ptr = nullptr;
+    s.bytes = 0;
+  }
+  JWC_CUDA(ctx, cudaMalloc(&s.ptr, bytes));
+  s.bytes = bytes;
+  return JWC_OK;
+}
+
+// BasicTransform.java:361-399 / :436-474.  forward: rows (axis 1, lvlN) then columns (axis 0,
+// lvlM); reverse: columns then rows.  Both passes run over the whole batch.
+static int t2d_dev(jwc_ctx* ctx, int wid, int kind, int dir, const double* in, double* out,
+                   int64_t batch, int rows, int cols, int lvlM, int lvlN) {
+  int st = check_common(ctx, wid, kind, dir, in, out);
+  if (st) return st;
+  // the reference transforms rows first (forward) / columns first (reverse): report in that order
+  if (dir == JWC_FORWARD) {
+    if ((st = check_axis(ctx, cols, lvlN)) || (st = check_axis(ctx, rows, lvlM))) return st;
+  } else {
+    if ((st = check_axis(ctx, rows, lvlM)) || (st = check_axis(ctx, cols, lvlN))) return st;
+  }
+  if (batch < 0) return fail(ctx, JWC_ERR_ARG, "negative batch");
+  if (batch == 0) return JWC_OK;
+  const int64_t total = batch * rows * cols;
+  if (overlaps(in, out, total)) return fail(ctx, JWC_ERR_ARG, "in and out overlap");
+  JWC_CUDA(ctx, cudaSetDevice(ctx->device));
+  if ((st = ensure(ctx, ctx->scratch[2], size_t(total) * sizeof(double)))) return st;
+  double* tmp = static_cast<double*>(ctx->scratch[2].ptr);
+  if (dir == JWC_FORWARD) {
+    if ((st = axis_dev(ctx, wid, kind, dir, in, tmp, batch * rows, cols, 1, lvlN))) return st;
+    return axis_dev(ctx, wid, kind, dir, tmp, out, batch, rows, cols, lvlM);
+  }
+  if ((st = axis_dev(ctx, wid, kind, dir, in, tmp, batch, rows, cols, lvlM))) return st;
+  return axis_dev(ctx, wid, kind, dir, tmp, out, batch * rows, cols, 1, lvlN);
+}
+
+extern "C" int jwc_fwt2d_dev(jwc_ctx* ctx, int wid, int dir, const double* in, double* out,
+                             int64_t batch, int rows, int cols, int lvlM, int lvlN) {
+  return t2d_dev(ctx, wid, JWC_FWT, dir, in, out, batch, rows, cols, lvlM, lvlN);
+}
+extern "C" int jwc_wpt2d_dev(jwc_ctx* ctx, int wid, int dir, const double* in, double* out,
+                             int64_t batch, int rows, int cols, int lvlM, int lvlN) {
+  return t2d_dev(ctx, wid, JWC_WPT, dir, in, out, batch, rows, cols, lvlM, lvlN);
+}
+
+// BasicTransform.java:509-566 / :602-659.  The 2-D call on each [j][k] slice receives
+// (lvlP, lvlQ) as (lvlM, lvlN): axis k (length R) gets lvlQ, axis j (length Q) gets lvlP; the
+// outer axis i (length P) gets lvlR.  forward: k, j, i.  reverse: j, k, i.
+static int t3d_dev(jwc_ctx* ctx, int wid, int kind, int dir, const double* in, double* out, int P,
+                   int Q, int R, int lvlP, int lvlQ, int lvlR) {
+  int st = check_common(ctx, wid, kind, dir, in, out);
+  if (st) return st;
+  if (dir == JWC_FORWARD) {
+    if ((st = check_axis(ctx, R, lvlQ)) || (st = check_axis(ctx, Q, lvlP))) return st;
+  } else {
+    if ((st = check_axis(ctx, Q, lvlP)) || (st = check_axis(ctx, R, lvlQ))) return st;
+  }
+  if ((st = check_axis(ctx, P, lvlR))) return st;
+  const int64_t total = int64_t(P) * Q * R;
+  if (overlaps(in, out, total)) return fail(ctx, JWC_ERR_ARG, "in and out overlap");
+  JWC_CUDA(ctx, cudaSetDevice(ctx->device));
+  if ((st = ensure(ctx, ctx->scratch[2], size_t(total) * sizeof(double)))) return st;
+  double* tmp = static_cast<double*>(ctx->scratch[2].ptr);
+  // in -> out -> tmp -> out
+  if (dir == JWC_FORWARD) {
+    if ((st = axis_dev(ctx, wid, kind, dir, in, out, int64_t(P) * Q, R, 1, lvlQ))) return st;
+    if ((st = axis_dev(ctx, wid, kind, dir, out, tmp, P, Q, R, lvlP))) return st;
+  } else {
+    if ((st = axis_dev(ctx, wid, kind, dir, in, out, P, Q, R, lvlP))) return st;
+    if ((st = axis_dev(ctx, wid, kind, dir, out, tmp, int64_t(P) * Q, R, 1, lvlQ))) return st;
+  }
+  return axis_dev(ctx, wid, kind, dir, tmp, out, 1, P, int64_t(Q) * R, lvlR);
+}
+
+extern "C" int jwc_fwt3d_dev(jwc_ctx* ctx, int wid, int dir, const double* in, double* out, int P,
+                             int Q, int R, int lvlP, int lvlQ, int lvlR) {
+  return t3d_dev(ctx, wid, JWC_FWT, dir, in, out, P, Q, R, lvlP, lvlQ, lvlR);
+}
+extern "C" int jwc_wpt3d_dev(jwc_ctx* ctx, int wid, int dir, const double* in, double* out, int P,
+                             int Q, int R, int lvlP, int lvlQ, int lvlR) {
+  return t3d_dev(ctx, wid, JWC_WPT, dir, in, out, P, Q, R, lvlP, lvlQ, lvlR);
+}
+
+// ---- host-buffer entry points ---------------------------------------------------------------------
+//
+// The batch is cut into chunks of whole items (signals / matrices); chunk c uses staging slot
+// c & 1, so the H2D copy of chunk c+1 and the D2H copy of chunk c-1 overlap the kernels of
+// chunk c (three streams, events between them).  Pinned host memory (jwc_host_alloc_pinned)
+// makes the copies truly asynchronous; pageable memory works, only slower.
+
+template <class Run>
+static int staged(jwc_ctx* ctx, const double* in, double* out, int64_t items, int64_t item_elems, Run run) {
+  if (items == 0) return JWC_OK;
+  JWC_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t item_bytes = size_t(item_elems) * sizeof(double);
+  int64_t per_chunk = int64_t(ctx->staging_bytes / item_bytes);
+  if (per_chunk < 1) per_chunk = 1;
+  if (per_chunk > items) per_chunk = items;
+  const int slots = per_chunk < items ? 2 : 1;
+  int st;
+  for (int s = 0; s < slots; ++s) {
+    if ((st = ensure(ctx, ctx->stage_in[s], size_t(per_chunk) * item_bytes))) return st;
+    if ((st = ensure(ctx, ctx->stage_out[s], size_t(per_chunk) * item_bytes))) return st;
+  }
+  cudaStream_t user_stream = ctx->stream;
+  ctx->stream = ctx->own_stream;  // the pipeline owns its three streams
+  int status = JWC_OK;
+  int64_t c = 0;
+  for (int64_t first = 0; first < items && !status; first += per_chunk, ++c) {
+    const int s = int(c % slots);
+    const int64_t cnt = (items - first < per_chunk) ? items - first : per_chunk;
+    double* d_in = static_cast<double*>(ctx->stage_in[s].ptr);
+    double* d_out = static_cast<double*>(ctx->stage_out[s].ptr);
+    cudaError_t e;
+    // slot reuse: the kernels that read d_in[s] and the D2H that read d_out[s] two chunks ago
+    if (c >= slots) {
+      if ((e = cudaStreamWaitEvent(ctx->h2d_stream, ctx->ev_done[s], 0)) != cudaSuccess) goto cuda_fail;
+      if ((e = cudaStreamWaitEvent(ctx->own_stream, ctx->ev_out[s], 0)) != cudaSuccess) goto cuda_fail;
+    }
+    if ((e = cudaMemcpyAsync(d_in, in + first * item_elems, size_t(cnt) * item_bytes, cudaMemcpyHostToDevice,
+                             ctx->h2d_stream)) != cudaSuccess) goto cuda_fail;
+    if ((e = cudaEventRecord(ctx->ev_in[s], ctx->h2d_stream)) != cudaSuccess) goto cuda_fail;
+    if ((e = cudaStreamWaitEvent(ctx->own_stream, ctx->ev_in[s], 0)) != cudaSuccess) goto cuda_fail;
+    status = run(d_in, d_out, cnt);
+    if (status) break;
+    if ((e = cudaEventRecord(ctx->ev_done[s], ctx->own_stream)) != cudaSuccess) goto cuda_fail;
+    if ((e = cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_done[s], 0)) != cudaSuccess) goto cuda_fail;
+    if ((e = cudaMemcpyAsync(out + first * item_elems, d_out, size_t(cnt) * item_bytes, cudaMemcpyDeviceToHost,
+                             ctx->d2h_stream)) != cudaSuccess) goto cuda_fail;
+    if ((e = cudaEventRecord(ctx->ev_out[s], ctx->d2h_stream)) != cudaSuccess) goto cuda_fail;
+    continue;
+  cuda_fail:
+    ctx->err = std::string("staging pipeline: ") + cudaGetErrorString(e);
+    status = JWC_ERR_CUDA;
+  }
+  cudaError_t e1 = cudaStreamSynchronize(ctx->h2d_stream);
+  cudaError_t e2 = cudaStreamSynchronize(ctx->own_stream);
+  cudaError_t e3 = cudaStreamSynchronize(ctx->d2h_stream);
+  ctx->stream = user_stream;
+  if (!status && (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)) {
+    cudaError_t e = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
+    ctx->err = std::string("staging pipeline: ") + cudaGetErrorString(e);
+    status = JWC_ERR_CUDA;
+  }
+  return status;
+}
+
+static int t1d_host(jwc_ctx* ctx, int wid, int kind, int dir, const double* in, double* out,
+                    int64_t batch, int n, int level) {
+  int st = check_common(ctx, wid, kind, dir, in, out);
+  if (st) return st;
+  if ((st = check_axis(ctx, n, level))) return st;
+  if (batch < 0) return fail(ctx, JWC_ERR_ARG, "negative batch");
+  return staged(ctx, in, out, batch, n, [&](const double* di, double* dout, int64_t cnt) {
+    return axis_dev(ctx, wid, kind, dir, di, dout, cnt, n, 1, level);
+  });
+}
+
+extern "C" int jwc_fwt1d(jwc_ctx* ctx, int wid, int dir, const double* in, double* out, int64_t batch,
+                         int n, int level) {
+  return t1d_host(ctx, wid, JWC_FWT, dir, in, out, batch, n, level);
+}
+extern "C" int jwc_wpt1d(jwc_ctx* ctx, int wid, int dir, const double* in, double* out, int64_t batch,
+                         int n, int level) {
+  return t1d_host(ctx, wid, JWC_WPT, dir, in, out, batch, n, level);
+}
+
+static int t2d_host(jwc_ctx* ctx, int wid, int kind, int dir, const double* in, double* out,
+                    int64_t batch, int rows, int cols, int lvlM, int lvlN) {
+  int st = check_common(ctx, wid, kind, dir, in, out);
+  if (st) return st;
+  if (dir == JWC_FORWARD) {
+    if ((st = check_axis(ctx, cols, lvlN)) || (st = check_axis(ctx, rows, lvlM))) return st;
+  } else {
+    if ((st = check_axis(ctx, rows, lvlM)) || (st = check_axis(ctx, cols, lvlN))) return st;
+  }
+  if (batch < 0) return fail(ctx, JWC_ERR_ARG, "negative batch");
+  return staged(ctx, in, out, batch, int64_t(rows) * cols, [&](const double* di, double* dout, int64_t cnt) {
+    return t2d_dev(ctx, wid, kind, dir, di, dout, cnt, rows, cols, lvlM, lvlN);
+  });
+}
+
+extern "C" int jwc_fwt2d(jwc_ctx* ctx, int wid, int dir, const double* in, double* out, int64_t batch,
+                         int rows, int cols, int lvlM, int lvlN) {
+  return t2d_host(ctx, wid, JWC_FWT, dir, in, out, batch, rows, cols, lvlM, lvlN);
+}
+extern "C" int jwc_wpt2d(jwc_ctx* ctx, int wid, int dir, const double* in, double* out, int64_t batch,
+                         int rows, int cols, int lvlM, int lvlN) {
+  return t2d_host(ctx, wid, JWC_WPT, dir, in, out, batch, rows, cols, lvlM, lvlN);
+}
+
+static int t3d_host(jwc_ctx* ctx, int wid, int kind, int dir, const double* in, double* out, int P,
+                    int Q, int R, int lvlP, int lvlQ, int lvlR) {
+  int st = check_common(ctx, wid, kind, dir, in, out);
+  if (st) return st;
+  if (P <= 0 || Q <= 0 || R <= 0) return fail(ctx, JWC_ERR_NOT_BINARY, "given array length is not 2^p | p E N");
+  const size_t keep = ctx->staging_bytes;
+  ctx->staging_bytes = size_t(-1) / 2;  // one volume is one item
+  st = staged(ctx, in, out, 1, int64_t(P) * Q * R, [&](const double* di, double* dout, int64_t) {
+    return t3d_dev(ctx, wid, kind, dir, di, dout, P, Q, R, lvlP, lvlQ, lvlR);
+  });
+  ctx->staging_bytes = keep;
+  return st;
+}
+
+extern "C" int jwc_fwt3d(jwc_ctx* ctx, int wid, int dir, const double* in, double* out, int P, int Q,
+                         int R, int lvlP, int lvlQ, int lvlR) {
+  return t3d_host(ctx, wid, JWC_FWT, dir, in, out, P, Q, R, lvlP, lvlQ, lvlR);
+}
+extern "C" int jwc_wpt3d(jwc_ctx* ctx, int wid, int dir, const double* in, double* out, int P, int Q,
+                         int R, int lvlP, int lvlQ, int lvlR) {
+  return t3d_host(ctx, wid, JWC_WPT, dir, in, out, P, Q, R, lvlP, lvlQ, lvlR);
+}
+
+// ---- memory helpers ----------------------------------------------------------------------------------
+
+extern "C" int jwc_dev_alloc(jwc_ctx* ctx, size_t bytes, void** dptr) {
+  if (!ctx || !dptr) return JWC_ERR_ARG;
+  JWC_CUDA(ctx, cudaSetDevice(ctx->device));
+  JWC_CUDA(ctx, cudaMalloc(dptr, bytes ? bytes : 1));
+  return JWC_OK;
+}
+extern "C" int jwc_dev_free(jwc_ctx* ctx, void* dptr) {
+  if (!ctx) return JWC_ERR_ARG;
+  JWC_CUDA(ctx, cudaSetDevice(ctx->device));
+  JWC_CUDA(ctx, cudaFree(dptr));
+  return JWC_OK;
+}
+extern "C" int jwc_h2d(jwc_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
+  if (!ctx || !dst_dev || !src_host) return JWC_ERR_ARG;
+  JWC_CUDA(ctx, cudaSetDevice(ctx->device));
+  JWC_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return JWC_OK;
+}
+extern "C" int jwc_d2h(jwc_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
+  if (!ctx || !dst_host || !src_dev) return JWC_ERR_ARG;
+  JWC_CUDA(ctx, cudaSetDevice(ctx->device));
+  JWC_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return JWC_OK;
+}
+extern "C" int jwc_host_alloc_pinned(jwc_ctx* ctx, size_t bytes, void** hptr) {
+  if (!ctx || !hptr) return JWC_ERR_ARG;
+  JWC_CUDA(ctx, cudaSetDevice(ctx->device));
+  JWC_CUDA(ctx, cudaHostAlloc(hptr, bytes ? bytes : 1, cudaHostAllocDefault));
+  return JWC_OK;
+}
+extern "C" int jwc_host_free_pinned(jwc_ctx* ctx, void* hptr) {
+  if (!ctx) return JWC_ERR_ARG;
+  JWC_CUDA(ctx, cudaFreeHost(hptr));
+  return JWC_OK;
+}
+extern "C" int jwc_set_staging_bytes(jwc_ctx* ctx, size_t bytes) {
+  if (!ctx || bytes < sizeof(double)) return JWC_ERR_ARG;
+  ctx->staging_bytes = bytes;
+  return JWC_OK;
+}

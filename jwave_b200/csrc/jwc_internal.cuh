@@ -1,0 +1,79 @@
+// jwc_internal.cuh - shared declarations of libjwave_cuda.so (not part of the public ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "jwave_cuda.h"
+
+namespace jwc {
+
+// One filter pair.  Passed BY VALUE as a __grid_constant__ kernel parameter, so the taps sit in
+// the constant bank and an unrolled `taps.lo[j]` becomes a c[0x0][imm] operand of the DFMA.
+struct Taps {
+  double lo[JWC_MAX_TAPS];  // scaling (low pass)
+  double hi[JWC_MAX_TAPS];  // wavelet (high pass)
+};
+
+struct WaveletRec {
+  int L;
+  Taps de;  // decomposition: _scalingDeCom / _waveletDeCom
+  Taps re;  // reconstruction: _scalingReCon / _waveletReCon
+};
+
+struct Scratch {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+};
+
+}  // namespace jwc
+
+struct jwc_ctx {
+  int device = 0;
+  int sm_count = 148;
+  size_t smem_optin = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;  // where kernels go (own_stream unless jwc_set_stream)
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  std::vector<jwc::WaveletRec> wavelets;
+  std::string err;
+  int64_t launches = 0;
+  jwc::Scratch scratch[4];      // [0],[1]: level ping-pong; [2]: axis ping-pong; [3]: alias guard
+  jwc::Scratch stage_in[2], stage_out[2];
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+  size_t staging_bytes = size_t(256) << 20;
+  bool force_generic = false;   // JWC_FORCE_GENERIC=1: only the one-level reference kernels
+};
+
+namespace jwc {
+
+// ---- geometry of one level over a set of lines ---------------------------------------------
+// A "line" is the 1-D sequence the transform runs along.  Element s of line (o, c) lives at
+//   base + o * os + s * inner + c,      o in [0, outer), c in [0, inner).
+// Contiguous signals have inner == 1; columns of a matrix have inner == cols.
+
+struct FwdLevelArgs {
+  const double* src; int64_t src_os;
+  double* dstA; int64_t dstA_os;
+  double* dstD; int64_t dstD_os;
+  int64_t outer; int64_t inner;
+  int half;  // outputs per line and filter: h / 2
+};
+
+struct RevLevelArgs {
+  const double* srcA; int64_t srcA_os;
+  const double* srcD; int64_t srcD_os;
+  double* dst; int64_t dst_os;
+  int64_t outer; int64_t inner;
+  int half;
+};
+
+// jwc_generic.cu: one level, any geometry, any width (exact modular wrap); the slow-but-always
+// -right kernels every other path is checked against and falls back to ON THE GPU.
+cudaError_t launch_fwd_level_generic(jwc_ctx* ctx, int L, const Taps& taps, const FwdLevelArgs& a);
+cudaError_t launch_rev_level_generic(jwc_ctx* ctx, int L, const Taps& taps, const RevLevelArgs& a);
+
+}  // namespace jwc

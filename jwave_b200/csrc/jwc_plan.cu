@@ -1,0 +1,151 @@
+// jwc_plan.cu - the level planner.
+//
+// Buffers.  The reference copies the input and then overwrites a shrinking / growing prefix
+// level by level (FastWaveletTransform.java:85-99).  On the GPU a level cannot run in place
+// (every output reads L inputs that other threads overwrite), so:
+//   FWT forward : details d_l go straight to their final place in `out`; approximations a_l
+//                 ping-pong between two compact scratch buffers; the last a_l lands in `out`.
+//   FWT reverse : d_l is read from `in`, the growing approximation ping-pongs in scratch and
+//                 the last level writes `out`.
+//   WPT         : whole-array ping-pong between `out` and one scratch buffer, phased so the
+//                 last level writes `out`.
+#include "jwc_plan.cuh"
+
+namespace jwc {
+
+cudaError_t ensure_scratch(jwc_ctx* ctx, int slot, size_t bytes, double** ptr) {
+  Scratch& s = ctx->scratch[slot];
+  if (s.bytes < bytes) {
+    cudaError_t e;
+    if (s.ptr) {
+      // earlier launches on the stream may still read the old block
+      if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return e;
+      if ((e = cudaFree(s.ptr)) != cudaSuccess) return e;
+      s.ptr = nullptr;
+      s.bytes = 0;
+    }
+    if ((e = cudaMalloc(&s.ptr, bytes)) != cudaSuccess) return e;
+    s.bytes = bytes;
+  }
+  *ptr = static_cast<double*>(s.ptr);
+  return cudaSuccess;
+}
+
+static cudaError_t copy_through(jwc_ctx* ctx, const double* in, double* out, int64_t count) {
+  return cudaMemcpyAsync(out, in, size_t(count) * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
+}
+
+#define JWC_TRY(call)                       \
+  do {                                      \
+    cudaError_t e__ = (call);               \
+    if (e__ != cudaSuccess) return e__;     \
+  } while (0)
+
+// ---- FWT ---------------------------------------------------------------------------------------
+
+static cudaError_t fwt_forward(jwc_ctx* ctx, const WaveletRec& w, const double* in, double* out,
+                               int64_t outer, int n, int64_t inner, int level) {
+  const int64_t line = int64_t(n) * inner;
+  double* S[2] = {nullptr, nullptr};
+  if (level >= 2) JWC_TRY(ensure_scratch(ctx, 1, size_t(outer) * (n / 2) * inner * sizeof(double), &S[1]));
+  if (level >= 3) JWC_TRY(ensure_scratch(ctx, 0, size_t(outer) * (n / 4) * inner * sizeof(double), &S[0]));
+  const double* src = in;
+  int64_t src_os = line;
+  int h = n;
+  for (int l = 1; l <= level; ++l) {
+    const int half = h >> 1;
+    const bool last = (l == level);
+    FwdLevelArgs a;
+    a.src = src; a.src_os = src_os;
+    a.dstA = last ? out : S[l & 1];
+    a.dstA_os = last ? line : int64_t(half) * inner;
+    a.dstD = out + int64_t(half) * inner;
+    a.dstD_os = line;
+    a.outer = outer; a.inner = inner; a.half = half;
+    JWC_TRY(launch_fwd_level_generic(ctx, w.L, w.de, a));
+    src = a.dstA; src_os = a.dstA_os; h = half;
+  }
+  return cudaSuccess;
+}
+
+static cudaError_t fwt_reverse(jwc_ctx* ctx, const WaveletRec& w, const double* in, double* out,
+                               int64_t outer, int n, int64_t inner, int level) {
+  const int64_t line = int64_t(n) * inner;
+  double* S[2] = {nullptr, nullptr};
+  if (level >= 2) JWC_TRY(ensure_scratch(ctx, 1, size_t(outer) * (n / 2) * inner * sizeof(double), &S[1]));
+  if (level >= 3) JWC_TRY(ensure_scratch(ctx, 0, size_t(outer) * (n / 4) * inner * sizeof(double), &S[0]));
+  // FastWaveletTransform.java:137-141: first width is 2 << (p - level)
+  const double* srcA = in;
+  int64_t srcA_os = line;
+  for (int l = level; l >= 1; --l) {
+    const int h = n >> (l - 1);  // width being rebuilt at this step
+    const int half = h >> 1;
+    const bool last = (l == 1);
+    RevLevelArgs a;
+    a.srcA = srcA; a.srcA_os = srcA_os;
+    a.srcD = in + int64_t(half) * inner; a.srcD_os = line;
+    // widths n/2, n/8, ... go to S[1] (n/2 per line), widths n/4, n/16, ... to S[0]
+    a.dst = last ? out : S[(l + 1) & 1];
+    a.dst_os = last ? line : int64_t(h) * inner;
+    a.outer = outer; a.inner = inner; a.half = half;
+    JWC_TRY(launch_rev_level_generic(ctx, w.L, w.re, a));
+    srcA = a.dst; srcA_os = a.dst_os;
+  }
+  return cudaSuccess;
+}
+
+// ---- WPT ---------------------------------------------------------------------------------------
+// At width h a line holds n / h packets; packet (o, q) starts at o*n*inner + q*h*inner, i.e. the
+// packets of all lines form `outer * n / h` lines of stride h * inner.
+
+static cudaError_t wpt_forward(jwc_ctx* ctx, const WaveletRec& w, const double* in, double* out,
+                               int64_t outer, int n, int64_t inner, int level) {
+  double* S = nullptr;
+  if (level >= 2) JWC_TRY(ensure_scratch(ctx, 0, size_t(outer) * n * inner * sizeof(double), &S));
+  const double* src = in;
+  int h = n;
+  for (int l = 1; l <= level; ++l) {
+    const int half = h >> 1;
+    double* dst = ((level - l) & 1) ? S : out;
+    FwdLevelArgs a;
+    a.src = src; a.src_os = int64_t(h) * inner;
+    a.dstA = dst; a.dstA_os = int64_t(h) * inner;
+    a.dstD = dst + int64_t(half) * inner; a.dstD_os = int64_t(h) * inner;
+    a.outer = outer * (n / h); a.inner = inner; a.half = half;
+    JWC_TRY(launch_fwd_level_generic(ctx, w.L, w.de, a));
+    src = dst; h = half;
+  }
+  return cudaSuccess;
+}
+
+static cudaError_t wpt_reverse(jwc_ctx* ctx, const WaveletRec& w, const double* in, double* out,
+                               int64_t outer, int n, int64_t inner, int level) {
+  double* S = nullptr;
+  if (level >= 2) JWC_TRY(ensure_scratch(ctx, 0, size_t(outer) * n * inner * sizeof(double), &S));
+  const double* src = in;
+  for (int l = level; l >= 1; --l) {
+    const int h = n >> (l - 1);
+    const int half = h >> 1;
+    double* dst = ((l - 1) & 1) ? S : out;
+    RevLevelArgs a;
+    a.srcA = src; a.srcA_os = int64_t(h) * inner;
+    a.srcD = src + int64_t(half) * inner; a.srcD_os = int64_t(h) * inner;
+    a.dst = dst; a.dst_os = int64_t(h) * inner;
+    a.outer = outer * (n / h); a.inner = inner; a.half = half;
+    JWC_TRY(launch_rev_level_generic(ctx, w.L, w.re, a));
+    src = dst;
+  }
+  return cudaSuccess;
+}
+
+cudaError_t run_axis(jwc_ctx* ctx, const WaveletRec& w, int kind, int dir, const double* in, double* out,
+                     int64_t outer, int n, int64_t inner, int level) {
+  if (level == 0 || n == 1) return copy_through(ctx, in, out, outer * n * inner);
+  if (kind == JWC_FWT)
+    return dir == JWC_FORWARD ? fwt_forward(ctx, w, in, out, outer, n, inner, level)
+                              : fwt_reverse(ctx, w, in, out, outer, n, inner, level);
+  return dir == JWC_FORWARD ? wpt_forward(ctx, w, in, out, outer, n, inner, level)
+                            : wpt_reverse(ctx, w, in, out, outer, n, inner, level);
+}
+
+}  // namespace jwc

@@ -1,0 +1,78 @@
+"""Device-resident entry points: torch CUDA tensors in, torch CUDA tensors out.
+
+torch is plumbing here (device memory, streams, torch.distributed); the arithmetic is
+libjwave_cuda.so's *_dev functions, enqueued on torch's current stream so torch.cuda.Event
+brackets them."""
+import torch
+
+from . import _lib
+from .exceptions import JWaveFailure
+from .transforms import CudaContext
+
+
+class DeviceTransforms:
+    """FWT / WPT over float64 CUDA tensors for one wavelet on one GPU."""
+
+    def __init__(self, wavelet, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("jwave_b200.device needs a CUDA device; there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.ctx = CudaContext(self.device.index)
+        self.wid = self.ctx.register(wavelet)
+        self.wavelet = wavelet
+        self._L = self.ctx._lib
+
+    def _prep(self, x, out):
+        if x.dtype != torch.float64 or not x.is_cuda or x.device != self.device:
+            raise JWaveFailure("expected a float64 tensor on " + str(self.device))
+        x = x.contiguous()
+        if out is None:
+            out = torch.empty_like(x)
+        elif out.shape != x.shape or out.dtype != x.dtype or out.device != x.device or not out.is_contiguous():
+            raise JWaveFailure("out must match the input (contiguous float64, same device)")
+        self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        return x, out
+
+    def axis(self, kind, direction, x, outer, n, inner, level, out=None):
+        """jwc_axis_dev on a dense [outer][n][inner] view of x."""
+        x, out = self._prep(x, out)
+        if outer * n * inner != x.numel():
+            raise JWaveFailure("outer * n * inner must equal the number of elements")
+        st = self._L.jwc_axis_dev(self.ctx.handle, self.wid, kind, direction, x.data_ptr(), out.data_ptr(),
+                                  outer, n, inner, level)
+        self.ctx.check(st, "jwc_axis_dev")
+        return out
+
+    def transform1d(self, kind, direction, x, level, out=None):
+        """x: [batch][n]"""
+        x, out = self._prep(x, out)
+        n = x.shape[-1]
+        fn = self._L.jwc_fwt1d_dev if kind == _lib.FWT else self._L.jwc_wpt1d_dev
+        st = fn(self.ctx.handle, self.wid, direction, x.data_ptr(), out.data_ptr(), x.numel() // n, n, level)
+        self.ctx.check(st, "jwc_1d_dev")
+        return out
+
+    def transform2d(self, kind, direction, x, lvlM, lvlN, out=None):
+        """x: [batch][rows][cols] (or [rows][cols])"""
+        x, out = self._prep(x, out)
+        rows, cols = x.shape[-2:]
+        fn = self._L.jwc_fwt2d_dev if kind == _lib.FWT else self._L.jwc_wpt2d_dev
+        st = fn(self.ctx.handle, self.wid, direction, x.data_ptr(), out.data_ptr(), x.numel() // (rows * cols),
+                rows, cols, lvlM, lvlN)
+        self.ctx.check(st, "jwc_2d_dev")
+        return out
+
+    def transform3d(self, kind, direction, x, lvlP, lvlQ, lvlR, out=None):
+        """x: [P][Q][R]"""
+        x, out = self._prep(x, out)
+        P, Q, R = x.shape
+        fn = self._L.jwc_fwt3d_dev if kind == _lib.FWT else self._L.jwc_wpt3d_dev
+        st = fn(self.ctx.handle, self.wid, direction, x.data_ptr(), out.data_ptr(), P, Q, R, lvlP, lvlQ, lvlR)
+        self.ctx.check(st, "jwc_3d_dev")
+        return out
+
+    def launch_count(self):
+        return self.ctx.launch_count()
+
+    def close(self):
+        self.ctx.close()

@@ -1,0 +1,227 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (host buffers) and through the
+device-resident entry points, against the CPU oracle on the same seeded inputs.
+
+Bar: max |gpu - cpu| <= 1e-12 * ||x||_inf for forward AND reverse, fp64,
+FMA / reordering permitted.  Round trips are held to 1e-10 only where the reference itself
+achieves it; elsewhere the GPU round trip must equal the CPU round trip."""
+import numpy as np
+import pytest
+
+import jwave_b200 as jw
+import reference_suite as rs
+from adapters import rng_signal
+from jwave_b200 import _lib
+from oracle import c_oracle as co
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-12
+ALL = list(jw.WAVELET_CLASSES)
+CONFIG_WAVELETS = ["Haar1", "Daubechies4", "Symlet8", "Daubechies20", "Coiflet5"]
+
+
+def make(kind, cls):
+    w = jw.WaveletBuilder.create(cls)
+    return jw.CudaFastWaveletTransform(w) if kind == "fwt" else jw.CudaWaveletPacketTransform(w)
+
+
+def okind(kind):
+    return co.FWT if kind == "fwt" else co.WPT
+
+
+def close(gpu, cpu, scale):
+    err = float(np.abs(gpu - cpu).max()) if gpu.size else 0.0
+    assert err <= REL * max(scale, 1e-300), f"max abs err {err:.3e} > {REL * scale:.3e}"
+
+
+# ---- the reference's own tests, run on the GPU ---------------------------------------------------
+
+def test_ref_haar_known_answer():
+    rs.check_haar_kat(make)
+
+
+@pytest.mark.parametrize("cls", rs.CREATE2ARR)
+def test_ref_stepping(cls):
+    rs.check_stepping(make, cls)
+
+
+@pytest.mark.parametrize("cls", CONFIG_WAVELETS + ["Coiflet1", "Symlet20"])
+def test_ref_decompose(cls):
+    rs.check_decompose(make, cls)
+
+
+@pytest.mark.parametrize("cls", CONFIG_WAVELETS + rs.LEGENDRE)
+def test_ref_rounding(cls):
+    rs.check_rounding(make, cls, fwt_iters=20, wpt_iters=6)
+
+
+@pytest.mark.parametrize("cls", rs.CREATE2ARR)
+def test_ref_general_example(cls):
+    rs.check_general_example(make, cls, n_random=1 << 16)
+
+
+def test_ref_sampling():
+    rs.check_sampling(make, n=1 << 20, oscillations=1024)
+
+
+def test_ref_properties():
+    rs.check_properties(make)
+
+
+def test_ref_error_paths():
+    rs.check_error_paths(make)
+
+
+# ---- parity against the oracle ---------------------------------------------------------------------
+
+@pytest.mark.parametrize("cls", ALL)
+@pytest.mark.parametrize("kind", ["fwt", "wpt"])
+def test_1d_parity_all_wavelets(kind, cls):
+    """Every in-scope wavelet, lengths 2 .. 4096 (so every h < L wrap case occurs), full depth
+    and partial levels, forward and reverse."""
+    t = make(kind, cls)
+    for n in (2, 4, 8, 32, 256, 4096):
+        x = rng_signal(n + 11, n)
+        p = n.bit_length() - 1
+        for level in sorted({p, 1, p // 2}):
+            cf = co.transform_1d(okind(kind), co.FORWARD, cls, x, level)
+            gf = t.forward(x, level)
+            close(gf, cf, np.abs(x).max())
+            close(t.reverse(cf, level), co.transform_1d(okind(kind), co.REVERSE, cls, cf, level), np.abs(cf).max())
+
+
+@pytest.mark.parametrize("cls", CONFIG_WAVELETS)
+@pytest.mark.parametrize("kind", ["fwt", "wpt"])
+def test_batch_parity(kind, cls):
+    """forwardBatch / reverseBatch on ragged batch sizes and the config lengths (2^14, 2^16)."""
+    t = make(kind, cls)
+    for batch, n, level in ((1, 1 << 16, None), (3, 1 << 14, None), (37, 512, 5), (130, 64, 6), (5, 1 << 16, 6)):
+        x = rng_signal(batch * 7 + n, batch, n)
+        lv = n.bit_length() - 1 if level is None else level
+        cf = co.batch_1d(okind(kind), co.FORWARD, cls, x, lv)
+        close(t.forwardBatch(x, lv), cf, np.abs(x).max())
+        close(t.reverseBatch(cf, lv), co.batch_1d(okind(kind), co.REVERSE, cls, cf, lv), np.abs(cf).max())
+    assert t.forwardBatch(np.empty((0, 64))).shape == (0, 64)  # empty batch
+
+
+def test_input_is_not_mutated_and_output_is_fresh():
+    t = make("fwt", "Daubechies4")
+    x = rng_signal(1, 1024)
+    keep = x.copy()
+    y = t.forward(x)
+    assert np.array_equal(x, keep) and y is not x  # FastWaveletTransform.java:85
+
+
+@pytest.mark.parametrize("kind", ["fwt", "wpt"])
+@pytest.mark.parametrize("cls", ["Haar1", "Daubechies4", "Daubechies20", "Coiflet5"])
+def test_2d_parity(kind, cls):
+    t = make(kind, cls)
+    for rows, cols, lv in ((64, 64, None), (16, 128, (2, 5)), (256, 8, (8, 0)), (1, 32, (0, 5)), (128, 256, None)):
+        m = rng_signal(rows * 3 + cols, rows, cols)
+        args = () if lv is None else lv
+        cf = co.transform_2d(okind(kind), co.FORWARD, cls, m, *args)
+        close(t.forward(m, *args), cf, np.abs(m).max())
+        close(t.reverse(cf, *args), co.transform_2d(okind(kind), co.REVERSE, cls, cf, *args), np.abs(cf).max())
+
+
+def test_2d_equals_row_by_row_composition():
+    """The whole-array 2-D pass equals BasicTransform's row-by-row driver over the GPU 1-D
+    transform (BasicTransform.java:361-399) - same kernels, so bit-equal up to tile effects."""
+    t = make("fwt", "Symlet8")
+    m = rng_signal(9, 32, 64)
+    whole = t.forward(m)
+    composed = jw.BasicTransform._forward2(t, m, 5, 6)
+    close(whole, composed, np.abs(m).max())
+
+
+def test_batched_2d_parity():
+    t = make("fwt", "Daubechies4")
+    mats = rng_signal(21, 5, 64, 128)
+    ref = np.stack([co.transform_2d(co.FWT, co.FORWARD, "Daubechies4", m) for m in mats])
+    close(t.forwardBatch2D(mats), ref, np.abs(mats).max())
+    close(t.reverseBatch2D(ref), mats, 1e3 * np.abs(mats).max())
+
+
+@pytest.mark.parametrize("kind", ["fwt", "wpt"])
+@pytest.mark.parametrize("cls", ["Haar1", "Coiflet5", "Daubechies4"])
+def test_3d_parity(kind, cls):
+    t = make(kind, cls)
+    for shape, lv in (((16, 16, 16), None), ((4, 8, 32), (3, 5, 2)), ((32, 4, 8), (1, 1, 1)), ((8, 8, 8), (0, 3, 0))):
+        s = rng_signal(sum(shape), *shape)
+        args = () if lv is None else lv
+        cf = co.transform_3d(okind(kind), co.FORWARD, cls, s, *args)
+        close(t.forward(s, *args), cf, np.abs(s).max())
+        close(t.reverse(cf, *args), co.transform_3d(okind(kind), co.REVERSE, cls, cf, *args), np.abs(cf).max())
+
+
+def test_3d_level_shift_is_reproduced():
+    """(lvlP, lvlQ, lvlR) = (4, 3, 2) on a 4 x 8 x 16 volume asks for 4 levels on
+    the length-8 axis -> JWaveFailure, exactly as the reference's driver would throw."""
+    t = make("fwt", "Haar1")
+    with pytest.raises(jw.JWaveFailure):
+        t.forward(rng_signal(2, 4, 8, 16), 4, 3, 2)
+
+
+def test_abi_status_codes():
+    """Raw C-ABI status codes (include/jwave_cuda.h) without the Python pre-checks."""
+    import ctypes as C
+    ctx = jw.CudaContext.default()
+    wid = ctx.register(jw.WaveletBuilder.create("Haar"))
+    L = ctx._lib
+    a = np.ones(100)
+    b = np.empty(100)
+    assert L.jwc_fwt1d(ctx.handle, wid, 0, a.ctypes.data, b.ctypes.data, 1, 100, 1) == _lib.ERR_NOT_BINARY
+    assert L.jwc_fwt1d(ctx.handle, wid, 0, a.ctypes.data, b.ctypes.data, 1, 64, 7) == _lib.ERR_LEVEL
+    assert L.jwc_fwt1d(ctx.handle, wid, 0, a.ctypes.data, b.ctypes.data, 1, 64, -1) == _lib.ERR_LEVEL
+    assert L.jwc_fwt1d(ctx.handle, 999, 0, a.ctypes.data, b.ctypes.data, 1, 64, 1) == _lib.ERR_ARG
+    assert L.jwc_fwt1d(ctx.handle, wid, 0, None, b.ctypes.data, 1, 64, 1) == _lib.ERR_ARG
+    assert L.jwc_fwt2d(ctx.handle, wid, 0, a.ctypes.data, b.ctypes.data, 1, 10, 10, 1, 1) == _lib.ERR_NOT_BINARY
+    assert L.jwc_fwt3d(ctx.handle, wid, 0, a.ctypes.data, b.ctypes.data, 4, 4, 4, 3, 1, 1) == _lib.ERR_LEVEL
+    odd = np.ones(3)
+    w = C.c_int()
+    dp = C.POINTER(C.c_double)
+    p = odd.ctypes.data_as(dp)
+    assert L.jwc_set_wavelet(ctx.handle, 3, p, p, p, p, C.byref(w)) == _lib.ERR_ARG
+    assert b"even" in L.jwc_last_error(ctx.handle)
+
+
+def test_device_resident_entry_points():
+    """torch tensors through the *_dev functions == host-buffer path (same kernels)."""
+    import torch
+    from jwave_b200.device import DeviceTransforms
+    w = jw.WaveletBuilder.create("Symlet8")
+    dev = DeviceTransforms(w)
+    host = jw.CudaWaveletPacketTransform(w)
+    x = rng_signal(5, 12, 4096)
+    xd = torch.from_numpy(x).cuda()
+    before = dev.launch_count()
+    yd = dev.transform1d(_lib.WPT, _lib.FORWARD, xd, 6)
+    assert dev.launch_count() > before
+    assert np.array_equal(yd.cpu().numpy(), host.forwardBatch(x, 6))
+    assert torch.equal(xd.cpu(), torch.from_numpy(x))
+    back = dev.transform1d(_lib.WPT, _lib.REVERSE, yd, 6)
+    close(back.cpu().numpy(), x, 1e2 * np.abs(x).max())
+    with pytest.raises(jw.JWaveFailure):  # overlap is refused
+        dev.transform1d(_lib.WPT, _lib.FORWARD, xd, 6, out=xd)
+    v = rng_signal(6, 8, 16, 32)
+    vd = torch.from_numpy(v).cuda()
+    fd = dev.transform3d(_lib.FWT, _lib.FORWARD, vd, 4, 5, 3)
+    close(fd.cpu().numpy(), co.transform_3d(co.FWT, co.FORWARD, "Symlet8", v, 4, 5, 3), np.abs(v).max())
+    # the axis primitive: middle axis of [outer][n][inner]
+    ax = dev.axis(_lib.FWT, _lib.FORWARD, vd, 8, 16, 32, 4)
+    ref = np.stack([co.transform_2d(co.FWT, co.FORWARD, "Symlet8", s, 4, 0) for s in v])
+    close(ax.cpu().numpy(), ref, np.abs(v).max())
+    dev.close()
+
+
+def test_staging_pipeline_chunks():
+    """Host path with a tiny staging chunk (many chunks, both slots reused) == one chunk."""
+    ctx = jw.CudaContext(0)
+    t = jw.CudaFastWaveletTransform(jw.WaveletBuilder.create("Daubechies4"), context=ctx)
+    x = rng_signal(8, 301, 256)
+    one = t.forwardBatch(x)
+    ctx.set_staging_bytes(256 * 8 * 7)  # 7 signals per chunk -> 43 chunks
+    many = t.forwardBatch(x)
+    assert np.array_equal(one, many)
+    close(one, co.batch_1d(co.FWT, co.FORWARD, "Daubechies4", x, 8), np.abs(x).max())
+    ctx.close()

@@ -1,0 +1,141 @@
+"""CPU tests: pin the oracle against every known-answer vector and analytic property the
+reference's own tests hold for this path, and against the independent
+numpy restatement (bit for bit)."""
+import numpy as np
+import pytest
+
+import reference_suite as rs
+from adapters import OracleFWT, OracleWPT, rng_signal
+from oracle import c_oracle as co
+from oracle import np_oracle as no
+
+
+def make(kind, cls):
+    return OracleFWT(cls) if kind == "fwt" else OracleWPT(cls)
+
+
+def test_registry_is_the_in_scope_set():
+    names = co.wavelet_names()
+    assert len(names) == 47 and len(set(names)) == 47
+    assert {"Haar1", "Daubechies4", "Symlet8", "Daubechies20", "Coiflet5", "Legendre3"} <= set(names)
+    for cls, L in (("Haar1", 2), ("Daubechies4", 8), ("Symlet8", 16), ("Coiflet5", 30), ("Daubechies20", 40)):
+        assert co.wavelet(cls).contents.motherWavelength == L
+
+
+def test_haar_known_answer():
+    rs.check_haar_kat(make)
+
+
+def test_filter_fixtures():
+    rs.check_haar_filters()
+
+
+@pytest.mark.parametrize("cls", co.wavelet_names())
+def test_tap_identities(cls):
+    """sum h = sqrt 2 (Legendre: -sqrt 2), g[i] = (-1)^i h[L-1-i], recon == decomp; and
+    sum h^2 = 1 plus double-shift orthogonality wherever SURVEY.md F8 says the table has them."""
+    s_de, w_de, s_re, w_re = co.wavelet(cls).contents.taps()
+    L = len(s_de)
+    sign = -1.0 if cls.startswith("Legendre") else 1.0
+    assert abs(s_de.sum() - sign * np.sqrt(2.0)) < 1e-9
+    assert np.array_equal(s_re, s_de) and np.array_equal(w_re, w_de)
+    assert np.array_equal(w_de, np.array([s_de[L - 1 - i] * (1 if i % 2 == 0 else -1) for i in range(L)]))
+    if cls in ("Legendre2", "Legendre3"):
+        assert abs((s_de ** 2).sum() - 1.0) > 0.3  # not orthonormal (F8): forward parity only
+        return
+    tol = 1e-6 if cls.startswith("Coiflet") else 1e-9
+    assert abs((s_de ** 2).sum() - 1.0) < tol
+    for k in range(1, L // 2):
+        assert abs(np.dot(s_de[2 * k:], s_de[: L - 2 * k])) < tol
+
+
+@pytest.mark.parametrize("cls", rs.CREATE2ARR)
+def test_stepping_ladder(cls):
+    rs.check_stepping(make, cls)
+
+
+@pytest.mark.parametrize("cls", rs.CREATE2ARR)
+def test_decompose_ladder(cls):
+    rs.check_decompose(make, cls)
+
+
+@pytest.mark.parametrize("cls", rs.CREATE2ARR + rs.LEGENDRE)
+def test_rounding(cls):
+    rs.check_rounding(make, cls, fwt_iters=20, wpt_iters=6)
+
+
+@pytest.mark.parametrize("cls", rs.CREATE2ARR)
+def test_general_example(cls):
+    rs.check_general_example(make, cls, n_random=1 << 12)
+
+
+def test_sampling():
+    rs.check_sampling(make)
+
+
+def test_properties():
+    rs.check_properties(make)
+
+
+def test_error_paths():
+    rs.check_error_paths(make)
+
+
+def test_parallel_equals_sequential_wpt():
+    """transforms/ParallelWPTTest.java:153-180 and ParallelWPTPerformanceTest.java:56-100: the
+    packet-parallel driver is the same arithmetic as WaveletPacketTransform (here: bit-equal)."""
+    for n, level in ((256, 4), (512, 5), (4096, 6)):
+        x = rng_signal(42, 5, n)
+        seq = co.transform_1d(co.WPT, co.FORWARD, "Daubechies4", x, level)
+        par = co.parallel_wpt(co.FORWARD, "Daubechies4", x, level, threads=4)
+        assert np.array_equal(seq, par)
+        assert np.array_equal(co.transform_1d(co.WPT, co.REVERSE, "Daubechies4", seq, level),
+                              co.parallel_wpt(co.REVERSE, "Daubechies4", par, level, threads=4))
+    with pytest.raises(co.OracleError):  # PooledWaveletPacketTransform.java:29
+        co.parallel_wpt(co.FORWARD, "Daubechies4", rng_signal(1, 2, 64), 0)
+
+
+@pytest.mark.parametrize("cls", co.wavelet_names())
+def test_c_oracle_equals_numpy_restatement(cls):
+    """Two independent restatements of Wavelet.java:236-303 + the level loops agree bit for bit."""
+    s = no.WAVELETS[cls]
+    for a, b in zip(co.wavelet(cls).contents.taps(), s):
+        assert np.array_equal(a, b)
+    for n in (2, 4, 16, 128):
+        x = rng_signal(n, n)
+        for level in (None, 1, max(0, n.bit_length() - 3)):
+            f = co.transform_1d(co.FWT, co.FORWARD, cls, x, level)
+            assert np.array_equal(f, no.fwt_forward(cls, x, level))
+            assert np.array_equal(co.transform_1d(co.FWT, co.REVERSE, cls, f, level), no.fwt_reverse(cls, f, level))
+            p = co.transform_1d(co.WPT, co.FORWARD, cls, x, level)
+            assert np.array_equal(p, no.wpt_forward(cls, x, level))
+            assert np.array_equal(co.transform_1d(co.WPT, co.REVERSE, cls, p, level), no.wpt_reverse(cls, p, level))
+
+
+@pytest.mark.parametrize("kind", ["fwt", "wpt"])
+def test_2d_3d_drivers_three_ways(kind):
+    """2-D / 3-D have no reference vectors.  Pin them by composition: the C
+    driver, the numpy driver and the product's BasicTransform host driver (with the oracle's
+    1-D transform plugged in) must agree bit for bit, including the 3-D level shift (F5)."""
+    k = co.FWT if kind == "fwt" else co.WPT
+    t = make(kind, "Coiflet2")
+    m = rng_signal(3, 8, 16)
+    for lv in ((3, 4), (1, 2), (0, 3)):
+        f = co.transform_2d(k, co.FORWARD, "Coiflet2", m, *lv)
+        assert np.array_equal(f, no.transform_2d(kind, "forward", "Coiflet2", m, *lv))
+        assert np.array_equal(f, t.forward(m, *lv))
+        r = co.transform_2d(k, co.REVERSE, "Coiflet2", f, *lv)
+        assert np.array_equal(r, no.transform_2d(kind, "reverse", "Coiflet2", f, *lv))
+        assert np.array_equal(r, t.reverse(f, *lv))
+    assert np.array_equal(co.transform_2d(k, co.FORWARD, "Coiflet2", m), t.forward(m))
+    s = rng_signal(4, 4, 8, 16)
+    for lv in ((3, 4, 2), (1, 2, 1)):  # (lvlP, lvlQ, lvlR): Q=8 gets lvlP, R=16 gets lvlQ, P=4 gets lvlR
+        f = co.transform_3d(k, co.FORWARD, "Coiflet2", s, *lv)
+        assert np.array_equal(f, no.transform_3d(kind, "forward", "Coiflet2", s, *lv))
+        assert np.array_equal(f, t.forward(s, *lv))
+        r = co.transform_3d(k, co.REVERSE, "Coiflet2", f, *lv)
+        assert np.array_equal(r, t.reverse(f, *lv))
+    with pytest.raises(co.OracleError):  # lvlP = 4 > log2(Q = 8): the shift makes this fail
+        co.transform_3d(k, co.FORWARD, "Coiflet2", s, 4, 3, 2)
+    c = rng_signal(5, 8, 8, 8)
+    assert np.array_equal(co.transform_3d(k, co.FORWARD, "Coiflet2", c), t.forward(c))
