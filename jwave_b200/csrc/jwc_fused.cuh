@@ -1,0 +1,83 @@
+// jwc_fused.cuh - device helpers shared by the fused (multi-level, shared-memory) kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "jwc_internal.cuh"
+
+namespace jwc {
+
+constexpr int kThreads = 256;  // CTA size of every fused kernel
+constexpr int kR = 4;          // consecutive outputs (per filter) one thread produces per step
+
+// Shared-memory layout of a line segment: interleaved samples as double2 (x[2k], x[2k+1]), one
+// pad slot after every 4 double2.  A thread that produces outputs 4g..4g+3 reads the window
+// k = 4g .. 4g + L/2 + 2; consecutive threads are 5 slots (80 B) apart, so the 8 lanes of a
+// quarter-warp LDS.128 phase hit 8 distinct 16-byte bank groups (20 t mod 32 words is a
+// permutation) - no bank conflicts.
+__device__ __forceinline__ int pad2(int k2) { return k2 + (k2 >> 2); }
+__host__ __device__ constexpr int pad2_size(int n2) { return n2 + (n2 >> 2) + 1; }
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// 256-bit global store / load of 4 consecutive doubles (32-byte aligned): STG.E.ENL2.256 on sm_100a.
+__device__ __forceinline__ void st_global_v4(double* p, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+__device__ __forceinline__ void ld_global_v4(const double* p, double& a, double& b, double& c, double& d) {
+  asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+
+// Forward step for 4 consecutive output pairs from a window held in shared memory.
+//   lo[r] = sum_j x[2(4g+r)+j] * taps.lo[j],  hi[r] likewise, j ascending (the reference's order,
+//   Wavelet.java:244-254, contracted to FMAs).
+// `win(q)` returns double2 number q of the window (q = 0 .. L/2 + 2).  Streaming over q keeps only
+// one double2 live besides the 8 accumulators, so register use does not grow with L.
+template <int L, class Win>
+__device__ __forceinline__ void fwd_step4(const Taps& taps, Win win, double (&lo)[kR], double (&hi)[kR]) {
+#pragma unroll
+  for (int r = 0; r < kR; ++r) lo[r] = hi[r] = 0.0;
+#pragma unroll
+  for (int q = 0; q < L / 2 + kR - 1; ++q) {
+    const double2 v = win(q);
+#pragma unroll
+    for (int r = 0; r < kR; ++r) {
+      const int jj = q - r;  // tap pair index for output r
+      if (jj >= 0 && jj < L / 2) {
+        lo[r] = fma(v.x, taps.lo[2 * jj], lo[r]);
+        hi[r] = fma(v.x, taps.hi[2 * jj], hi[r]);
+        lo[r] = fma(v.y, taps.lo[2 * jj + 1], lo[r]);
+        hi[r] = fma(v.y, taps.hi[2 * jj + 1], hi[r]);
+      }
+    }
+  }
+}
+
+// Reverse step (gather form of Wavelet.java:288-299) for 4 consecutive coefficient slots
+// p = 4g .. 4g+3, i.e. 8 consecutive time samples t[8g .. 8g+7]:
+//   t[2p+r] = sum_q a[p-q] * lo[2q+r] + d[p-q] * hi[2q+r],   q = 0 .. L/2-1
+// `ca(s)` / `cd(s)` return a[4g + 3 - s] / d[4g + 3 - s] for s = 0 .. L/2 + 2 (walking left).
+template <int L, class Ca, class Cd>
+__device__ __forceinline__ void rev_step4(const Taps& taps, Ca ca, Cd cd, double (&t)[2 * kR]) {
+#pragma unroll
+  for (int r = 0; r < 2 * kR; ++r) t[r] = 0.0;
+#pragma unroll
+  for (int s = 0; s < L / 2 + kR - 1; ++s) {
+    const double av = ca(s), dv = cd(s);
+#pragma unroll
+    for (int pp = 0; pp < kR; ++pp) {
+      const int q = s - (kR - 1 - pp);  // a[4g+3-s] = a[(4g+pp) - q]
+      if (q >= 0 && q < L / 2) {
+        t[2 * pp] = fma(av, taps.lo[2 * q], t[2 * pp]);
+        t[2 * pp] = fma(dv, taps.hi[2 * q], t[2 * pp]);
+        t[2 * pp + 1] = fma(av, taps.lo[2 * q + 1], t[2 * pp + 1]);
+        t[2 * pp + 1] = fma(dv, taps.hi[2 * q + 1], t[2 * pp + 1]);
+      }
+    }
+  }
+}
+
+}  // namespace jwc

@@ -1,0 +1,28 @@
+// jwc_kernels.cuh - argument blocks and host launchers of the fused kernels.
+#pragma once
+#include "jwc_internal.cuh"
+
+namespace jwc {
+
+// every even filter length in scope: Haar1 (2) .. Daubechies20 / Symlet20 (40)
+#define JWC_FOR_EACH_L(X) \
+  X(2) X(4) X(6) X(8) X(10) X(12) X(14) X(16) X(18) X(20) X(22) X(24) X(26) X(28) X(30) X(32) X(34) X(36) X(38) X(40)
+
+constexpr int kTile = 4096;  // level-0 samples per CTA in tile mode; largest resident line
+
+// ---- forward FWT, contiguous lines (jwc_fwt_fwd.cu) -----------------------------------------
+struct FwtFwdArgs {
+  const double* src; int64_t src_os;    // input lines of width h (stride between lines, in doubles)
+  double* dstD; int64_t dstD_os;        // final output lines: d_k lands at line + (h >> k) + ...
+  double* dstA; int64_t dstA_os;        // where a_m goes (compact scratch or the final output)
+  int64_t lines;
+  int h;                                // current width
+  int m;                                // levels fused in this launch
+  int T;                                // tile length (tile mode)
+  int G;                                // lines per CTA (resident mode)
+  int tiles_per_line, cap0, cap1;       // filled in by the launcher
+};
+int fwt_tile_levels(int L, int T);
+cudaError_t launch_fwt_fwd(jwc_ctx* ctx, int L, const Taps& taps, const FwtFwdArgs& a, bool resident);
+
+}  // namespace jwc

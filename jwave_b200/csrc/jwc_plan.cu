@@ -11,6 +11,8 @@
 //                 last level writes `out`.
 #include "jwc_plan.cuh"
 
+#include "jwc_kernels.cuh"
+
 namespace jwc {
 
 cudaError_t ensure_scratch(jwc_ctx* ctx, int slot, size_t bytes, double** ptr) {
@@ -43,8 +45,16 @@ static cudaError_t copy_through(jwc_ctx* ctx, const double* in, double* out, int
 
 // ---- FWT ---------------------------------------------------------------------------------------
 
-static cudaError_t fwt_forward(jwc_ctx* ctx, const WaveletRec& w, const double* in, double* out,
-                               int64_t outer, int n, int64_t inner, int level) {
+static bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; }
+
+// The fused kernels use 16-byte cp.async and 32-byte vector stores: contiguous lines whose
+// bases are 32-byte aligned (true for every n >= 4 on a 32-byte aligned allocation).
+static bool fused_ok(const jwc_ctx* ctx, const double* in, const double* out, int n, int64_t inner) {
+  return !ctx->force_generic && inner == 1 && n >= 4 && aligned32(in) && aligned32(out);
+}
+
+static cudaError_t fwt_forward_generic(jwc_ctx* ctx, const WaveletRec& w, const double* in, double* out,
+                                       int64_t outer, int n, int64_t inner, int level) {
   const int64_t line = int64_t(n) * inner;
   double* S[2] = {nullptr, nullptr};
   if (level >= 2) JWC_TRY(ensure_scratch(ctx, 1, size_t(outer) * (n / 2) * inner * sizeof(double), &S[1]));
@@ -64,6 +74,39 @@ static cudaError_t fwt_forward(jwc_ctx* ctx, const WaveletRec& w, const double* 
     a.outer = outer; a.inner = inner; a.half = half;
     JWC_TRY(launch_fwd_level_generic(ctx, w.L, w.de, a));
     src = a.dstA; src_os = a.dstA_os; h = half;
+  }
+  return cudaSuccess;
+}
+
+// Fused plan: tile passes of m levels each while the width exceeds kTile, then one resident
+// launch for everything that is left.  a_m of a tile pass goes to a compact scratch buffer.
+static cudaError_t fwt_forward(jwc_ctx* ctx, const WaveletRec& w, const double* in, double* out,
+                               int64_t outer, int n, int64_t inner, int level) {
+  if (!fused_ok(ctx, in, out, n, inner)) return fwt_forward_generic(ctx, w, in, out, outer, n, inner, level);
+  const int m_tile = fwt_tile_levels(w.L, kTile);
+  double* S[2] = {nullptr, nullptr};
+  if (n > kTile && level > m_tile) {
+    JWC_TRY(ensure_scratch(ctx, 1, size_t(outer) * (n >> m_tile) * sizeof(double), &S[1]));
+    if ((n >> m_tile) > kTile && level > 2 * m_tile)
+      JWC_TRY(ensure_scratch(ctx, 0, size_t(outer) * (n >> (2 * m_tile)) * sizeof(double), &S[0]));
+  }
+  FwtFwdArgs a;
+  a.src = in; a.src_os = n;
+  a.dstD = out; a.dstD_os = n;
+  a.lines = outer;
+  int h = n, left = level, pass = 0;
+  while (left > 0) {
+    const bool resident = (h <= kTile);
+    a.h = h;
+    a.T = resident ? h : kTile;
+    a.m = resident ? left : (left < m_tile ? left : m_tile);
+    a.G = resident ? kTile / h : 1;
+    const bool last = (a.m == left);
+    a.dstA = last ? out : S[(pass + 1) & 1];
+    a.dstA_os = last ? n : (h >> a.m);
+    JWC_TRY(launch_fwt_fwd(ctx, w.L, w.de, a, resident));
+    a.src = a.dstA; a.src_os = a.dstA_os;
+    h >>= a.m; left -= a.m; ++pass;
   }
   return cudaSuccess;
 }
