@@ -65,8 +65,11 @@ int jwc_destroy(jwc_ctx* ctx);
 const char* jwc_last_error(const jwc_ctx* ctx);
 
 /* Launch on a caller-owned cudaStream_t (e.g. torch's current stream) instead of the context's
- * own.  Pass NULL to go back to the context's stream. */
+ * own.  The handle is used as given: NULL is CUDA's legacy default stream.  jwc_reset_stream goes
+ * back to the context's own stream.  The host-buffer entry points always use the context's own
+ * streams and are synchronous on return. */
 int jwc_set_stream(jwc_ctx* ctx, void* cuda_stream);
+int jwc_reset_stream(jwc_ctx* ctx);
 int jwc_sync(jwc_ctx* ctx);
 /* Number of kernels this context has launched so far. */
 int64_t jwc_launch_count(const jwc_ctx* ctx);

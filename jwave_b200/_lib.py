@@ -25,6 +25,7 @@ SIGNATURES = {
     "jwc_destroy": (_int, [_vp]),
     "jwc_last_error": (C.c_char_p, [_vp]),
     "jwc_set_stream": (_int, [_vp, _vp]),
+    "jwc_reset_stream": (_int, [_vp]),
     "jwc_sync": (_int, [_vp]),
     "jwc_launch_count": (_i64, [_vp]),
     "jwc_set_wavelet": (_int, [_vp, _int, _dp, _dp, _dp, _dp, C.POINTER(_int)]),

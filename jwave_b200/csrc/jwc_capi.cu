@@ -115,7 +115,13 @@ extern "C" const char* jwc_last_error(const jwc_ctx* ctx) {
 
 extern "C" int jwc_set_stream(jwc_ctx* ctx, void* cuda_stream) {
   if (!ctx) return JWC_ERR_ARG;
-  ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+  ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+  return JWC_OK;
+}
+
+extern "C" int jwc_reset_stream(jwc_ctx* ctx) {
+  if (!ctx) return JWC_ERR_ARG;
+  ctx->stream = ctx->own_stream;
   return JWC_OK;
 }
 
@@ -326,6 +332,8 @@ static int staged(jwc_ctx* ctx, const double* in, double* out, int64_t items, in
     if ((st = ensure(ctx, ctx->stage_out[s], size_t(per_chunk) * item_bytes))) return st;
   }
   cudaStream_t user_stream = ctx->stream;
+  if (user_stream != ctx->own_stream)  // device-resident work may still be using the scratch buffers
+    JWC_CUDA(ctx, cudaStreamSynchronize(user_stream));
   ctx->stream = ctx->own_stream;  // the pipeline owns its three streams
   int status = JWC_OK;
   int64_t c = 0;

@@ -1,0 +1,249 @@
+// jwc_fwt_rev.cu - fused multi-level reverse FWT along contiguous lines.
+//
+// Replaces the level loop of FastWaveletTransform.reverse (FastWaveletTransform.java:143-149)
+// around Wavelet.reverse (Wavelet.java:277-303) for `m` consecutive levels per launch.  The
+// reference's scatter `t[(2i+j) mod h] += a[i] s[j] + d[i] w[j]` is evaluated as a gather
+// (jwc_fused.cuh: rev_step8), so no atomics and no zero-fill are needed.
+//
+// Launch-level numbering: level 0 is the output of the launch (width h0), level m its coarsest
+// input a_m (width h0 >> m); d_k (width h0 >> k) sits at `srcD + (h0 >> k)` in every line,
+// which is where the FWT layout [a_l | d_l | ... | d_1] keeps it.
+//
+//   resident mode (h0 <= kTile): G whole lines per CTA, wrap by index mask, every level down to
+//                                h = 2 (a scalar path covers widths below 16).
+//   tile mode     (h0  > kTile): one CTA = T output samples.  Level k needs a_k / d_k only
+//                                N_k = F_k + L/2 - 1 coefficients to the LEFT of the tile (F_k = 8-aligned
+//                                extension computed at that level, < L) - the halo does not grow
+//                                geometrically as it does in the forward direction.
+#include "jwc_fused.cuh"
+#include "jwc_kernels.cuh"
+
+namespace jwc {
+
+constexpr int kRS = 8;  // coefficient slots (=> 16 time samples) per thread and step
+
+// 8 consecutive slots p = 8g' .. 8g'+7 -> t[16]:  t[2pp+r] = sum_q a[p-q] lo[2q+r] + d[p-q] hi[2q+r].
+// `a2(w)` / `d2(w)` return double2 number (4g' + 3 - w) of the a / d arrays, w = 0 .. L/4 + 3.
+template <int L, class A2, class D2>
+__device__ __forceinline__ void rev_step8(const Taps& taps, A2 a2, D2 d2, double (&t)[2 * kRS]) {
+#pragma unroll
+  for (int r = 0; r < 2 * kRS; ++r) t[r] = 0.0;
+  constexpr int W = (L / 2) / 2 + 4;
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    const double2 av = a2(w), dv = d2(w);
+#pragma unroll
+    for (int pp = 0; pp < kRS; ++pp) {
+      const int qy = pp - 7 + 2 * w;  // .y is slot 8g'+7-2w
+      const int qx = qy + 1;          // .x is slot 8g'+6-2w
+      if (qy >= 0 && qy < L / 2) {
+        t[2 * pp] = fma(av.y, taps.lo[2 * qy], t[2 * pp]);
+        t[2 * pp] = fma(dv.y, taps.hi[2 * qy], t[2 * pp]);
+        t[2 * pp + 1] = fma(av.y, taps.lo[2 * qy + 1], t[2 * pp + 1]);
+        t[2 * pp + 1] = fma(dv.y, taps.hi[2 * qy + 1], t[2 * pp + 1]);
+      }
+      if (qx >= 0 && qx < L / 2) {
+        t[2 * pp] = fma(av.x, taps.lo[2 * qx], t[2 * pp]);
+        t[2 * pp] = fma(dv.x, taps.hi[2 * qx], t[2 * pp]);
+        t[2 * pp + 1] = fma(av.x, taps.lo[2 * qx + 1], t[2 * pp + 1]);
+        t[2 * pp + 1] = fma(dv.x, taps.hi[2 * qx + 1], t[2 * pp + 1]);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ double sm_scalar(const double2* buf, int i) {
+  return reinterpret_cast<const double*>(buf)[2 * pad2(i >> 1) + (i & 1)];
+}
+__device__ __forceinline__ void sm_scalar_store(double2* buf, int i, double v) {
+  reinterpret_cast<double*>(buf)[2 * pad2(i >> 1) + (i & 1)] = v;
+}
+
+template <int L, bool RESIDENT>
+__global__ void __launch_bounds__(kThreads)
+k_fwt_rev(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevArgs a) {
+  extern __shared__ double2 smem2[];
+  const int tid = threadIdx.x;
+  const int m = a.m, h0 = a.h0;
+
+  if constexpr (!RESIDENT) {
+    // ---------------- tile mode ----------------
+    const int64_t line = blockIdx.x / a.tiles_per_line;
+    const int tile = int(blockIdx.x % a.tiles_per_line);
+    const int T = a.T;
+    const int t0 = tile * T;
+    const double* lineD = a.srcD + line * a.srcD_os;
+    // stage d_k (k = 1..m) and a_m; local sample j of level k is absolute slot O_k + j (periodic)
+    for (int k = 1; k <= m; ++k) {
+      const int wk = h0 >> k;  // width of a_k and d_k
+      const int O = (k == m) ? ((t0 >> k) - a.F[k] - a.ru8) : 2 * ((t0 >> (k + 1)) - a.F[k + 1]);
+      double2* D = smem2 + a.offD[k];
+      const double* dk = lineD + wk;
+      for (int j2 = tid; j2 < a.len[k] / 2; j2 += kThreads)
+        cp_async16(&D[pad2(j2)], dk + ((O + 2 * j2) & (wk - 1)));
+      if (k == m) {
+        double2* A = smem2 + a.offA[m & 1];
+        const double* am = a.srcA + line * a.srcA_os;
+        for (int j2 = tid; j2 < a.len[k] / 2; j2 += kThreads)
+          cp_async16(&A[pad2(j2)], am + ((O + 2 * j2) & (wk - 1)));
+      }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+
+    for (int k = m; k >= 1; --k) {
+      const double2* A = smem2 + a.offA[k & 1];
+      const double2* D = smem2 + a.offD[k];
+      double2* Y = smem2 + a.offA[(k - 1) & 1];
+      const int groups = ((T >> k) + a.F[k]) / kRS;
+      const int g0 = a.g0[k];
+      for (int g = tid; g < groups; g += kThreads) {
+        double t[2 * kRS];
+        const int c = 4 * (g + g0) + 3;
+        rev_step8<L>(taps, [&](int w) { return A[pad2(c - w)]; }, [&](int w) { return D[pad2(c - w)]; }, t);
+        if (k > 1) {
+#pragma unroll
+          for (int e = 0; e < kRS; ++e) Y[pad2(kRS * g + e)] = make_double2(t[2 * e], t[2 * e + 1]);
+        } else {
+          double* y = a.dst + line * a.dst_os + t0 + 2 * kRS * g;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) st_global_v4(y + 4 * e, t[4 * e], t[4 * e + 1], t[4 * e + 2], t[4 * e + 3]);
+        }
+      }
+      __syncthreads();
+    }
+  } else {
+    // ---------------- resident mode ----------------
+    const int G = a.G;
+    const int64_t line0 = int64_t(blockIdx.x) * G;
+    const int nlines = int(min(int64_t(G), a.lines - line0));
+    const int capC = a.capC, capP0 = a.capP[0], capP1 = a.capP[1];
+    double2* C = smem2;                                  // coefficient prefix [a_m | d_m | ... | d_1]
+    double2* P[2] = {smem2 + size_t(G) * capC, smem2 + size_t(G) * (capC + capP0)};  // a_k: P[k & 1]
+    const int capP[2] = {capP0, capP1};
+    {
+      const int per_line = h0 >> 1;
+      for (int it = tid; it < nlines * per_line; it += kThreads) {
+        const int ln = it / per_line, k2 = it - ln * per_line;
+        cp_async16(&C[ln * capC + pad2(k2)], a.srcD + (line0 + ln) * a.srcD_os + 2 * k2);
+      }
+      cp_async_wait_all();
+      __syncthreads();
+    }
+    for (int k = m; k >= 1; --k) {
+      const int half = h0 >> k;  // length of a_k and d_k
+      const bool from_c = (k == m);
+      const bool last = (k == 1);
+      if (half >= kRS) {
+        const int gpl = half / kRS;
+        const int mask2 = (half >> 1) - 1;
+        const int doff = half >> 1;  // d_k starts at sample `half` of the prefix
+        for (int it = tid; it < nlines * gpl; it += kThreads) {
+          const int ln = it / gpl, g = it - ln * gpl;
+          const double2* cl = C + ln * capC;
+          const double2* al = from_c ? cl : P[k & 1] + ln * capP[k & 1];
+          const int c = 4 * g + 3;
+          double t[2 * kRS];
+          rev_step8<L>(taps, [&](int w) { return al[pad2((c - w) & mask2)]; },
+                       [&](int w) { return cl[pad2(doff + ((c - w) & mask2))]; }, t);
+          if (!last) {
+            double2* y = P[(k - 1) & 1] + ln * capP[(k - 1) & 1];
+#pragma unroll
+            for (int e = 0; e < kRS; ++e) y[pad2(kRS * g + e)] = make_double2(t[2 * e], t[2 * e + 1]);
+          } else {
+            double* y = a.dst + (line0 + ln) * a.dst_os + 2 * kRS * g;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) st_global_v4(y + 4 * e, t[4 * e], t[4 * e + 1], t[4 * e + 2], t[4 * e + 3]);
+          }
+        }
+      } else {
+        // widths 2, 4, 8: one thread per (line, slot), true modular indexing (h < L wraps)
+        const int mask = half - 1;
+        for (int it = tid; it < nlines * half; it += kThreads) {
+          const int ln = it / half, p = it - ln * half;
+          const double2* cl = C + ln * capC;
+          const double2* al = from_c ? cl : P[k & 1] + ln * capP[k & 1];
+          double t0v = 0.0, t1v = 0.0;
+#pragma unroll
+          for (int q = 0; q < L / 2; ++q) {
+            const int i = (p - q) & mask;
+            const double av = sm_scalar(al, i), dv = sm_scalar(cl, half + i);
+            t0v = fma(av, taps.lo[2 * q], t0v);
+            t0v = fma(dv, taps.hi[2 * q], t0v);
+            t1v = fma(av, taps.lo[2 * q + 1], t1v);
+            t1v = fma(dv, taps.hi[2 * q + 1], t1v);
+          }
+          if (!last) {
+            P[(k - 1) & 1][ln * capP[(k - 1) & 1] + pad2(p)] = make_double2(t0v, t1v);
+          } else {
+            double* y = a.dst + (line0 + ln) * a.dst_os + 2 * p;
+            y[0] = t0v;
+            y[1] = t1v;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+
+static int round_up8(int v) { return (v + 7) & ~7; }
+
+template <int L>
+static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, FwtRevArgs a, bool resident) {
+  size_t smem;
+  int grid;
+  if (!resident) {
+    if (a.m < 1 || a.m > kMaxFuse || (a.T >> a.m) < kRS) return cudaErrorInvalidValue;
+    a.ru8 = round_up8(L / 2 - 1);
+    int N = 0;  // N_{k-1}: left extension of a_{k-1} the level below needs
+    for (int k = 1; k <= a.m; ++k) {
+      a.F[k] = round_up8((N + 1) / 2);
+      N = a.F[k] + L / 2 - 1;
+    }
+    a.F[a.m + 1] = 0;
+    int off = 0;
+    int capA[2] = {0, 0};
+    for (int k = 1; k <= a.m; ++k) {
+      a.len[k] = (k == a.m) ? (a.T >> k) + a.F[k] + a.ru8 : (a.T >> k) + 2 * a.F[k + 1];
+      a.g0[k] = (k == a.m) ? a.ru8 / kRS : (2 * a.F[k + 1] - a.F[k]) / kRS;
+      a.offD[k] = off;
+      off += pad2_size(a.len[k] / 2);
+      if (pad2_size(a.len[k] / 2) > capA[k & 1]) capA[k & 1] = pad2_size(a.len[k] / 2);
+    }
+    a.offA[0] = off;
+    a.offA[1] = off + capA[0];
+    smem = size_t(off + capA[0] + capA[1]) * sizeof(double2);
+    a.tiles_per_line = a.h0 / a.T;
+    const int64_t ctas = a.lines * a.tiles_per_line;
+    if (ctas > 0x7fffffff) return cudaErrorInvalidConfiguration;
+    grid = int(ctas);
+  } else {
+    a.capC = pad2_size(a.h0 / 2);
+    a.capP[1] = pad2_size(max(1, a.h0 / 4));  // a_1 (odd levels): h0 / 2 samples
+    a.capP[0] = pad2_size(max(1, a.h0 / 8));  // a_2 (even levels): h0 / 4 samples
+    smem = size_t(a.G) * (a.capC + a.capP[0] + a.capP[1]) * sizeof(double2);
+    grid = int((a.lines + a.G - 1) / a.G);
+  }
+  auto kern = resident ? k_fwt_rev<L, true> : k_fwt_rev<L, false>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return e;
+  }
+  kern<<<grid, kThreads, smem, ctx->stream>>>(taps, a);
+  ctx->launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fwt_rev(jwc_ctx* ctx, int L, const Taps& taps, const FwtRevArgs& a, bool resident) {
+  switch (L) {
+#define JWC_CASE(LL) case LL: return launch_L<LL>(ctx, taps, a, resident);
+    JWC_FOR_EACH_L(JWC_CASE)
+#undef JWC_CASE
+  }
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace jwc

@@ -25,4 +25,20 @@ struct FwtFwdArgs {
 int fwt_tile_levels(int L, int T);
 cudaError_t launch_fwt_fwd(jwc_ctx* ctx, int L, const Taps& taps, const FwtFwdArgs& a, bool resident);
 
+// ---- reverse FWT, contiguous lines (jwc_fwt_rev.cu) -----------------------------------------
+constexpr int kMaxFuse = 12;
+constexpr int kRevTileLevels = 6;
+struct FwtRevArgs {
+  const double* srcA; int64_t srcA_os;  // a_m lines (width h0 >> m); resident mode reads a_m from srcD
+  const double* srcD; int64_t srcD_os;  // coefficient lines: d_k at line + (h0 >> k)
+  double* dst; int64_t dst_os;          // a_0 lines (width h0)
+  int64_t lines;
+  int h0, m, T, G;
+  // filled in by the launcher
+  int tiles_per_line, ru8;
+  int F[kMaxFuse + 2], g0[kMaxFuse + 1], len[kMaxFuse + 1], offD[kMaxFuse + 1], offA[2];
+  int capC, capP[2];
+};
+cudaError_t launch_fwt_rev(jwc_ctx* ctx, int L, const Taps& taps, const FwtRevArgs& a, bool resident);
+
 }  // namespace jwc

@@ -111,8 +111,8 @@ static cudaError_t fwt_forward(jwc_ctx* ctx, const WaveletRec& w, const double* 
   return cudaSuccess;
 }
 
-static cudaError_t fwt_reverse(jwc_ctx* ctx, const WaveletRec& w, const double* in, double* out,
-                               int64_t outer, int n, int64_t inner, int level) {
+static cudaError_t fwt_reverse_generic(jwc_ctx* ctx, const WaveletRec& w, const double* in, double* out,
+                                       int64_t outer, int n, int64_t inner, int level) {
   const int64_t line = int64_t(n) * inner;
   double* S[2] = {nullptr, nullptr};
   if (level >= 2) JWC_TRY(ensure_scratch(ctx, 1, size_t(outer) * (n / 2) * inner * sizeof(double), &S[1]));
@@ -133,6 +133,56 @@ static cudaError_t fwt_reverse(jwc_ctx* ctx, const WaveletRec& w, const double* 
     a.outer = outer; a.inner = inner; a.half = half;
     JWC_TRY(launch_rev_level_generic(ctx, w.L, w.re, a));
     srcA = a.dst; srcA_os = a.dst_os;
+  }
+  return cudaSuccess;
+}
+
+// Fused plan: one resident launch rebuilds everything up to width kTile, then tile passes of up
+// to kRevTileLevels levels each.  Intermediate approximations go to compact scratch lines.
+static cudaError_t fwt_reverse(jwc_ctx* ctx, const WaveletRec& w, const double* in, double* out,
+                               int64_t outer, int n, int64_t inner, int level) {
+  if (!fused_ok(ctx, in, out, n, inner)) return fwt_reverse_generic(ctx, w, in, out, outer, n, inner, level);
+  struct Pass { int h0, m; bool resident; };
+  Pass passes[32];
+  int npass = 0;
+  size_t need[2] = {0, 0};
+  for (int cur = n >> level; cur < n;) {
+    Pass p;
+    if (2 * cur <= kTile) {
+      p.h0 = n < kTile ? n : kTile;
+      p.resident = true;
+    } else {
+      int m = 0;
+      while ((cur << m) < n && m < kRevTileLevels) ++m;
+      p.h0 = cur << m;
+      p.resident = false;
+    }
+    p.m = 0;
+    while ((cur << p.m) < p.h0) ++p.m;
+    if (p.h0 < n) {
+      const size_t bytes = size_t(outer) * p.h0 * sizeof(double);
+      if (bytes > need[npass & 1]) need[npass & 1] = bytes;
+    }
+    passes[npass++] = p;
+    cur = p.h0;
+  }
+  double* S[2] = {nullptr, nullptr};
+  for (int i = 0; i < 2; ++i)
+    if (need[i]) JWC_TRY(ensure_scratch(ctx, i, need[i], &S[i]));
+  FwtRevArgs a;
+  a.srcA = in; a.srcA_os = n;
+  a.srcD = in; a.srcD_os = n;
+  a.lines = outer;
+  for (int i = 0; i < npass; ++i) {
+    const Pass& p = passes[i];
+    const bool last = (p.h0 == n);
+    a.h0 = p.h0; a.m = p.m;
+    a.T = p.resident ? p.h0 : kTile;
+    a.G = p.resident ? kTile / p.h0 : 1;
+    a.dst = last ? out : S[i & 1];
+    a.dst_os = last ? n : p.h0;
+    JWC_TRY(launch_fwt_rev(ctx, w.L, w.re, a, p.resident));
+    a.srcA = a.dst; a.srcA_os = a.dst_os;
   }
   return cudaSuccess;
 }

@@ -93,7 +93,11 @@ class CudaContext:
         return int(self._lib.jwc_launch_count(self.handle))
 
     def set_stream(self, cuda_stream):
+        """Use the given cudaStream_t handle (0 = CUDA's legacy default stream) for *_dev calls."""
         self.check(self._lib.jwc_set_stream(self.handle, C.c_void_p(cuda_stream or 0)), "jwc_set_stream")
+
+    def reset_stream(self):
+        self.check(self._lib.jwc_reset_stream(self.handle), "jwc_reset_stream")
 
     def sync(self):
         self.check(self._lib.jwc_sync(self.handle), "jwc_sync")
