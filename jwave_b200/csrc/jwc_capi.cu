@@ -76,6 +76,20 @@ extern "C" int jwc_create(jwc_ctx** out, int device) {
   ctx->stream = ctx->own_stream;
   const char* fg = getenv("JWC_FORCE_GENERIC");
   ctx->force_generic = fg && fg[0] == '1';
+  if (const char* tune = getenv("JWC_TUNE")) {
+    auto get = [&](const char* key, int* dst) {
+      const char* p = strstr(tune, key);
+      if (p && p[strlen(key)] == '=') {
+        const int v = atoi(p + strlen(key) + 1);
+        if (v > 0) *dst = v;
+      }
+    };
+    get("fwd_tile", &ctx->fwd_tile);
+    get("fwd_m", &ctx->fwd_m);
+    get("rev_tile", &ctx->rev_tile);
+    get("rev_m", &ctx->rev_m);
+    get("res_cap", &ctx->res_cap);
+  }
   *out = ctx;
   return JWC_OK;
 }

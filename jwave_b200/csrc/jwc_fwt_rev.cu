@@ -99,8 +99,10 @@ k_fwt_rev(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevArgs 
       const int g0 = a.g0[k];
       for (int g = tid; g < groups; g += kThreads) {
         double t[2 * kRS];
-        const int c = 4 * (g + g0) + 3;
-        rev_step8<L>(taps, [&](int w) { return A[pad2(c - w)]; }, [&](int w) { return D[pad2(c - w)]; }, t);
+        // pad2(4g' + 3 - w) = 5g' + (3 - w) + floor((3 - w) / 4): a compile-time offset per w
+        const int base = 5 * (g + g0);
+        rev_step8<L>(taps, [&](int w) { return A[base + (3 - w) + ((3 - w) >> 2)]; },
+                     [&](int w) { return D[base + (3 - w) + ((3 - w) >> 2)]; }, t);
         if (k > 1) {
 #pragma unroll
           for (int e = 0; e < kRS; ++e) Y[pad2(kRS * g + e)] = make_double2(t[2 * e], t[2 * e + 1]);

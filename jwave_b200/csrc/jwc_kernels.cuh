@@ -8,7 +8,6 @@ namespace jwc {
 #define JWC_FOR_EACH_L(X) \
   X(2) X(4) X(6) X(8) X(10) X(12) X(14) X(16) X(18) X(20) X(22) X(24) X(26) X(28) X(30) X(32) X(34) X(36) X(38) X(40)
 
-constexpr int kTile = 4096;  // level-0 samples per CTA in tile mode; largest resident line
 
 // ---- forward FWT, contiguous lines (jwc_fwt_fwd.cu) -----------------------------------------
 struct FwtFwdArgs {
@@ -27,7 +26,6 @@ cudaError_t launch_fwt_fwd(jwc_ctx* ctx, int L, const Taps& taps, const FwtFwdAr
 
 // ---- reverse FWT, contiguous lines (jwc_fwt_rev.cu) -----------------------------------------
 constexpr int kMaxFuse = 12;
-constexpr int kRevTileLevels = 6;
 struct FwtRevArgs {
   const double* srcA; int64_t srcA_os;  // a_m lines (width h0 >> m); resident mode reads a_m from srcD
   const double* srcD; int64_t srcD_os;  // coefficient lines: d_k at line + (h0 >> k)

@@ -83,11 +83,13 @@ static cudaError_t fwt_forward_generic(jwc_ctx* ctx, const WaveletRec& w, const 
 static cudaError_t fwt_forward(jwc_ctx* ctx, const WaveletRec& w, const double* in, double* out,
                                int64_t outer, int n, int64_t inner, int level) {
   if (!fused_ok(ctx, in, out, n, inner)) return fwt_forward_generic(ctx, w, in, out, outer, n, inner, level);
-  const int m_tile = fwt_tile_levels(w.L, kTile);
+  const int cap = ctx->res_cap, tileT = ctx->fwd_tile;
+  int m_tile = fwt_tile_levels(w.L, tileT);
+  if (ctx->fwd_m > 0 && ctx->fwd_m < m_tile) m_tile = ctx->fwd_m;
   double* S[2] = {nullptr, nullptr};
-  if (n > kTile && level > m_tile) {
+  if (n > cap && level > m_tile) {
     JWC_TRY(ensure_scratch(ctx, 1, size_t(outer) * (n >> m_tile) * sizeof(double), &S[1]));
-    if ((n >> m_tile) > kTile && level > 2 * m_tile)
+    if ((n >> m_tile) > cap && level > 2 * m_tile)
       JWC_TRY(ensure_scratch(ctx, 0, size_t(outer) * (n >> (2 * m_tile)) * sizeof(double), &S[0]));
   }
   FwtFwdArgs a;
@@ -96,11 +98,11 @@ static cudaError_t fwt_forward(jwc_ctx* ctx, const WaveletRec& w, const double* 
   a.lines = outer;
   int h = n, left = level, pass = 0;
   while (left > 0) {
-    const bool resident = (h <= kTile);
+    const bool resident = (h <= cap);
     a.h = h;
-    a.T = resident ? h : kTile;
+    a.T = resident ? h : tileT;
     a.m = resident ? left : (left < m_tile ? left : m_tile);
-    a.G = resident ? kTile / h : 1;
+    a.G = resident ? cap / h : 1;
     const bool last = (a.m == left);
     a.dstA = last ? out : S[(pass + 1) & 1];
     a.dstA_os = last ? n : (h >> a.m);
@@ -146,17 +148,24 @@ static cudaError_t fwt_reverse(jwc_ctx* ctx, const WaveletRec& w, const double* 
   Pass passes[32];
   int npass = 0;
   size_t need[2] = {0, 0};
-  for (int cur = n >> level; cur < n;) {
+  // Output widths of the passes, chosen backwards from n: every tile pass rebuilds
+  // kRevTileLevels levels, so the resident pass ends at n >> (6 * tile passes) (a few hundred
+  // samples per line, many lines per CTA) and the scratch round trip stays below 2 / 64 of the data.
+  int widths[32];
+  int nw = 0;
+  const int cur0 = n >> level;
+  const int cap = ctx->res_cap;
+  int rev_m = ctx->rev_m;
+  while ((ctx->rev_tile >> rev_m) < 8) --rev_m;  // a tile keeps >= 8 slots at its coarsest level
+  for (int wv = n; wv > cur0; wv >>= rev_m) {
+    widths[nw++] = wv;
+    if (wv <= cap) break;  // this one is produced by the resident pass
+    if ((wv >> rev_m) <= cur0) break;
+  }
+  for (int i = nw - 1, cur = cur0; i >= 0; --i) {
     Pass p;
-    if (2 * cur <= kTile) {
-      p.h0 = n < kTile ? n : kTile;
-      p.resident = true;
-    } else {
-      int m = 0;
-      while ((cur << m) < n && m < kRevTileLevels) ++m;
-      p.h0 = cur << m;
-      p.resident = false;
-    }
+    p.h0 = widths[i];
+    p.resident = (p.h0 <= cap);
     p.m = 0;
     while ((cur << p.m) < p.h0) ++p.m;
     if (p.h0 < n) {
@@ -177,8 +186,8 @@ static cudaError_t fwt_reverse(jwc_ctx* ctx, const WaveletRec& w, const double* 
     const Pass& p = passes[i];
     const bool last = (p.h0 == n);
     a.h0 = p.h0; a.m = p.m;
-    a.T = p.resident ? p.h0 : kTile;
-    a.G = p.resident ? kTile / p.h0 : 1;
+    a.T = p.resident ? p.h0 : ctx->rev_tile;
+    a.G = p.resident ? cap / p.h0 : 1;
     a.dst = last ? out : S[i & 1];
     a.dst_os = last ? n : p.h0;
     JWC_TRY(launch_fwt_rev(ctx, w.L, w.re, a, p.resident));
