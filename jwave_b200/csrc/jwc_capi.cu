@@ -81,7 +81,7 @@ extern "C" int jwc_create(jwc_ctx** out, int device) {
       const char* p = strstr(tune, key);
       if (p && p[strlen(key)] == '=') {
         const int v = atoi(p + strlen(key) + 1);
-        if (v > 0) *dst = v;
+        if (v >= 0) *dst = v;
       }
     };
     get("fwd_tile", &ctx->fwd_tile);

@@ -4,10 +4,10 @@
 // around Wavelet.forward (Wavelet.java:236-260) for `m` consecutive levels per launch: the
 // intermediate approximations a_1 .. a_{m-1} live only in shared memory.
 //
-//   tile mode      (h > kTile)  : one CTA = one tile of T level-0 samples of one line plus a
+//   tile mode      (h > res_cap) : one CTA = one tile of T level-0 samples of one line plus a
 //                                 right-hand periodic halo of (2^m - 1)(L - 2) samples; details
 //                                 d_1..d_m go to their final place, a_m to `dstA`.
-//   resident mode  (h <= kTile) : one CTA = G whole lines; the periodic wrap is an index mask, so
+//   resident mode  (h <= res_cap): one CTA = G whole lines; the periodic wrap is an index mask, so
 //                                 every remaining level (down to h = 2) runs in this launch.
 //
 // HBM traffic per launch: h samples read (+ halo re-reads that hit L2), h samples written.

@@ -9,9 +9,9 @@
 // input a_m (width h0 >> m); d_k (width h0 >> k) sits at `srcD + (h0 >> k)` in every line,
 // which is where the FWT layout [a_l | d_l | ... | d_1] keeps it.
 //
-//   resident mode (h0 <= kTile): G whole lines per CTA, wrap by index mask, every level down to
+//   resident mode (h0 <= res_cap): G whole lines per CTA, wrap by index mask, every level down to
 //                                h = 2 (a scalar path covers widths below 16).
-//   tile mode     (h0  > kTile): one CTA = T output samples.  Level k needs a_k / d_k only
+//   tile mode     (h0  > res_cap): one CTA = T output samples.  Level k needs a_k / d_k only
 //                                N_k = F_k + L/2 - 1 coefficients to the LEFT of the tile (F_k = 8-aligned
 //                                extension computed at that level, < L) - the halo does not grow
 //                                geometrically as it does in the forward direction.

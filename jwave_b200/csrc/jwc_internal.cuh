@@ -46,8 +46,8 @@ struct jwc_ctx {
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
   size_t staging_bytes = size_t(256) << 20;
   bool force_generic = false;   // JWC_FORCE_GENERIC=1: only the one-level reference kernels
-  // launch-shape tunables (JWC_TUNE="fwd_tile=2048,fwd_m=5,rev_tile=2048,rev_m=6,res_cap=4096")
-  int fwd_tile = 4096, fwd_m = 0 /* 0 = from the halo rule */, rev_tile = 4096, rev_m = 6, res_cap = 4096;
+  // launch-shape tunables (JWC_TUNE="fwd_tile=2048,fwd_m=5,rev_tile=4096,rev_m=5,res_cap=4096")
+  int fwd_tile = 2048, fwd_m = 0 /* 0 = from the halo rule */, rev_tile = 4096, rev_m = 5, res_cap = 4096;
 };
 
 namespace jwc {

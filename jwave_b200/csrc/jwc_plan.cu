@@ -78,7 +78,7 @@ static cudaError_t fwt_forward_generic(jwc_ctx* ctx, const WaveletRec& w, const 
   return cudaSuccess;
 }
 
-// Fused plan: tile passes of m levels each while the width exceeds kTile, then one resident
+// Fused plan: tile passes of m levels each while the width exceeds res_cap, then one resident
 // launch for everything that is left.  a_m of a tile pass goes to a compact scratch buffer.
 static cudaError_t fwt_forward(jwc_ctx* ctx, const WaveletRec& w, const double* in, double* out,
                                int64_t outer, int n, int64_t inner, int level) {
@@ -139,8 +139,8 @@ static cudaError_t fwt_reverse_generic(jwc_ctx* ctx, const WaveletRec& w, const 
   return cudaSuccess;
 }
 
-// Fused plan: one resident launch rebuilds everything up to width kTile, then tile passes of up
-// to kRevTileLevels levels each.  Intermediate approximations go to compact scratch lines.
+// Fused plan: one resident launch rebuilds everything up to width res_cap, then tile passes of up
+// to rev_m levels each.  Intermediate approximations go to compact scratch lines.
 static cudaError_t fwt_reverse(jwc_ctx* ctx, const WaveletRec& w, const double* in, double* out,
                                int64_t outer, int n, int64_t inner, int level) {
   if (!fused_ok(ctx, in, out, n, inner)) return fwt_reverse_generic(ctx, w, in, out, outer, n, inner, level);
@@ -149,7 +149,7 @@ static cudaError_t fwt_reverse(jwc_ctx* ctx, const WaveletRec& w, const double* 
   int npass = 0;
   size_t need[2] = {0, 0};
   // Output widths of the passes, chosen backwards from n: every tile pass rebuilds
-  // kRevTileLevels levels, so the resident pass ends at n >> (6 * tile passes) (a few hundred
+  // rev_m levels, so the resident pass ends at n >> (rev_m * tile passes) (a few hundred
   // samples per line, many lines per CTA) and the scratch round trip stays below 2 / 64 of the data.
   int widths[32];
   int nw = 0;
