@@ -89,6 +89,7 @@ extern "C" int jwc_create(jwc_ctx** out, int device) {
     get("rev_tile", &ctx->rev_tile);
     get("rev_m", &ctx->rev_m);
     get("res_cap", &ctx->res_cap);
+    get("wpt_tile", &ctx->wpt_tile);
   }
   *out = ctx;
   return JWC_OK;

@@ -17,6 +17,14 @@ constexpr int kR = 4;          // consecutive outputs (per filter) one thread pr
 __device__ __forceinline__ int pad2(int k2) { return k2 + (k2 >> 2); }
 __host__ __device__ constexpr int pad2_size(int n2) { return n2 + (n2 >> 2) + 1; }
 
+// scalar view of a padded double2 line
+__device__ __forceinline__ double sm_scalar(const double2* buf, int i) {
+  return reinterpret_cast<const double*>(buf)[2 * pad2(i >> 1) + (i & 1)];
+}
+__device__ __forceinline__ void sm_scalar_store(double2* buf, int i, double v) {
+  reinterpret_cast<double*>(buf)[2 * pad2(i >> 1) + (i & 1)] = v;
+}
+
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src) : "memory");

@@ -52,13 +52,6 @@ __device__ __forceinline__ void rev_step8(const Taps& taps, A2 a2, D2 d2, double
   }
 }
 
-__device__ __forceinline__ double sm_scalar(const double2* buf, int i) {
-  return reinterpret_cast<const double*>(buf)[2 * pad2(i >> 1) + (i & 1)];
-}
-__device__ __forceinline__ void sm_scalar_store(double2* buf, int i, double v) {
-  reinterpret_cast<double*>(buf)[2 * pad2(i >> 1) + (i & 1)] = v;
-}
-
 template <int L, bool RESIDENT>
 __global__ void __launch_bounds__(kThreads)
 k_fwt_rev(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevArgs a) {

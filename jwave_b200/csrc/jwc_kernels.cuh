@@ -39,4 +39,28 @@ struct FwtRevArgs {
 };
 cudaError_t launch_fwt_rev(jwc_ctx* ctx, int L, const Taps& taps, const FwtRevArgs& a, bool resident);
 
+// ---- forward WPT, contiguous lines (jwc_wpt_fwd.cu) -----------------------------------------
+struct WptFwdArgs {
+  const double* src; int64_t src_os;    // input lines (packets of width h)
+  double* dst; int64_t dst_os;          // output lines: 2^m leaf packets of width h >> m, natural order
+  int64_t lines;
+  int h, m, T, G;
+  int tiles_per_line, buf_cap;          // filled in by the launcher
+};
+int wpt_tile_levels(int L, int T, int want, size_t smem_limit);
+cudaError_t launch_wpt_fwd(jwc_ctx* ctx, int L, const Taps& taps, const WptFwdArgs& a, bool resident);
+
+// ---- reverse WPT, contiguous lines (jwc_wpt_rev.cu) -----------------------------------------
+struct WptRevArgs {
+  const double* src; int64_t src_os;    // input lines: 2^m leaf packets of width h0 >> m
+  double* dst; int64_t dst_os;          // output lines (one packet of width h0)
+  int64_t lines;
+  int h0, m, T, G;
+  // filled in by the launcher
+  int tiles_per_line, ru8, buf_cap;
+  int F[kMaxFuse + 2], g0[kMaxFuse + 1], len[kMaxFuse + 1], cap[kMaxFuse + 1];
+};
+int wpt_rev_tile_levels(int L, int T, int want, size_t smem_limit);
+cudaError_t launch_wpt_rev(jwc_ctx* ctx, int L, const Taps& taps, const WptRevArgs& a, bool resident);
+
 }  // namespace jwc

@@ -200,8 +200,8 @@ static cudaError_t fwt_reverse(jwc_ctx* ctx, const WaveletRec& w, const double* 
 // At width h a line holds n / h packets; packet (o, q) starts at o*n*inner + q*h*inner, i.e. the
 // packets of all lines form `outer * n / h` lines of stride h * inner.
 
-static cudaError_t wpt_forward(jwc_ctx* ctx, const WaveletRec& w, const double* in, double* out,
-                               int64_t outer, int n, int64_t inner, int level) {
+static cudaError_t wpt_forward_generic(jwc_ctx* ctx, const WaveletRec& w, const double* in, double* out,
+                                       int64_t outer, int n, int64_t inner, int level) {
   double* S = nullptr;
   if (level >= 2) JWC_TRY(ensure_scratch(ctx, 0, size_t(outer) * n * inner * sizeof(double), &S));
   const double* src = in;
@@ -220,8 +220,8 @@ static cudaError_t wpt_forward(jwc_ctx* ctx, const WaveletRec& w, const double* 
   return cudaSuccess;
 }
 
-static cudaError_t wpt_reverse(jwc_ctx* ctx, const WaveletRec& w, const double* in, double* out,
-                               int64_t outer, int n, int64_t inner, int level) {
+static cudaError_t wpt_reverse_generic(jwc_ctx* ctx, const WaveletRec& w, const double* in, double* out,
+                                       int64_t outer, int n, int64_t inner, int level) {
   double* S = nullptr;
   if (level >= 2) JWC_TRY(ensure_scratch(ctx, 0, size_t(outer) * n * inner * sizeof(double), &S));
   const double* src = in;
@@ -236,6 +236,86 @@ static cudaError_t wpt_reverse(jwc_ctx* ctx, const WaveletRec& w, const double* 
     a.outer = outer * (n / h); a.inner = inner; a.half = half;
     JWC_TRY(launch_rev_level_generic(ctx, w.L, w.re, a));
     src = dst;
+  }
+  return cudaSuccess;
+}
+
+// Fused WPT plans.  A pass of m levels turns every packet of width h into 2^m packets of width
+// h >> m, so the next pass sees 2^m times as many, shorter lines.  Whole-array ping-pong between
+// `out` and one scratch buffer, phased so the last pass writes `out`.
+static const size_t kWptSmemLimit = 112 * 1024;  // two CTAs per SM
+
+static cudaError_t wpt_forward(jwc_ctx* ctx, const WaveletRec& w, const double* in, double* out,
+                               int64_t outer, int n, int64_t inner, int level) {
+  if (!fused_ok(ctx, in, out, n, inner) || n < 8) return wpt_forward_generic(ctx, w, in, out, outer, n, inner, level);
+  struct Pass { int h, m; bool resident; };
+  Pass passes[32];
+  int npass = 0;
+  for (int h = n, left = level; left > 0;) {
+    Pass p;
+    p.h = h;
+    p.resident = (h <= ctx->res_cap);
+    p.m = p.resident ? left : wpt_tile_levels(w.L, ctx->wpt_tile, left, kWptSmemLimit);
+    passes[npass++] = p;
+    h >>= p.m; left -= p.m;
+  }
+  double* S = nullptr;
+  if (npass >= 2) JWC_TRY(ensure_scratch(ctx, 0, size_t(outer) * n * sizeof(double), &S));
+  const double* src = in;
+  for (int i = 0; i < npass; ++i) {
+    const Pass& p = passes[i];
+    WptFwdArgs a;
+    a.src = src; a.src_os = p.h;
+    a.dst = ((npass - 1 - i) & 1) ? S : out; a.dst_os = p.h;
+    a.lines = outer * (n / p.h);
+    a.h = p.h; a.m = p.m;
+    a.T = p.resident ? p.h : ctx->wpt_tile;
+    a.G = p.resident ? ctx->res_cap / p.h : 1;
+    JWC_TRY(launch_wpt_fwd(ctx, w.L, w.de, a, p.resident));
+    src = a.dst;
+  }
+  return cudaSuccess;
+}
+
+static cudaError_t wpt_reverse(jwc_ctx* ctx, const WaveletRec& w, const double* in, double* out,
+                               int64_t outer, int n, int64_t inner, int level) {
+  if (!fused_ok(ctx, in, out, n, inner) || n < 8) return wpt_reverse_generic(ctx, w, in, out, outer, n, inner, level);
+  // output widths of the passes: the first (resident) pass rebuilds packets up to res_cap, tile
+  // passes take it from there
+  struct Pass { int h0, m; bool resident; };
+  Pass passes[32];
+  int npass = 0;
+  for (int cur = n >> level; cur < n;) {
+    Pass p;
+    if (2 * cur <= ctx->res_cap) {
+      p.h0 = n < ctx->res_cap ? n : ctx->res_cap;
+      p.resident = true;
+      p.m = 0;
+      while ((cur << p.m) < p.h0) ++p.m;
+    } else {
+      int want = 0;
+      while ((cur << want) < n) ++want;
+      p.m = wpt_rev_tile_levels(w.L, ctx->wpt_tile, want, kWptSmemLimit);
+      p.h0 = cur << p.m;
+      p.resident = false;
+    }
+    passes[npass++] = p;
+    cur = p.h0;
+  }
+  double* S = nullptr;
+  if (npass >= 2) JWC_TRY(ensure_scratch(ctx, 0, size_t(outer) * n * sizeof(double), &S));
+  const double* src = in;
+  for (int i = 0; i < npass; ++i) {
+    const Pass& p = passes[i];
+    WptRevArgs a;
+    a.src = src; a.src_os = p.h0;
+    a.dst = ((npass - 1 - i) & 1) ? S : out; a.dst_os = p.h0;
+    a.lines = outer * (n / p.h0);
+    a.h0 = p.h0; a.m = p.m;
+    a.T = p.resident ? p.h0 : ctx->wpt_tile;
+    a.G = p.resident ? ctx->res_cap / p.h0 : 1;
+    JWC_TRY(launch_wpt_rev(ctx, w.L, w.re, a, p.resident));
+    src = a.dst;
   }
   return cudaSuccess;
 }

@@ -1,0 +1,256 @@
+// jwc_wpt_rev.cu - fused multi-level reverse wavelet PACKET transform along contiguous lines.
+//
+// Replaces the level x packet loops of WaveletPacketTransform.reverse
+// (WaveletPacketTransform.java:164-187; Pooled / Parallel variants:
+// PooledWaveletPacketTransform.java:74-127, ParallelWaveletPacketTransform.java:113-146) around
+// Wavelet.reverse (Wavelet.java:277-303), `m` levels per launch, gather form (jwc_fwt_rev.cu).
+//
+// Launch-level numbering: level 0 is the output (one packet of width h0 per line), level m the
+// input: 2^m leaf packets of width h0 >> m, stored back to back in natural order.  Nodes 2j and
+// 2j+1 of level k are the approximation / detail halves that rebuild node j of level k-1.
+//
+//   tile mode     (h0  > res_cap): one CTA = T output samples; every node of level k needs only
+//                                  N_k = F_k + L/2 - 1 coefficients left of the tile (see jwc_fwt_rev.cu).
+//   resident mode (h0 <= res_cap): G whole lines per CTA, wrap by index mask; nodes shorter than 8
+//                                  take a scalar path with true modular indexing.
+#include "jwc_fused.cuh"
+#include "jwc_kernels.cuh"
+
+namespace jwc {
+
+constexpr int kRS = 8;  // coefficient slots (=> 16 time samples) per thread and step
+
+// identical to jwc_fwt_rev.cu: 8 slots p = 8g'..8g'+7 -> t[16]; a2(w)/d2(w) = double2 (4g'+3-w)
+template <int L, class A2, class D2>
+__device__ __forceinline__ void rev_step8(const Taps& taps, A2 a2, D2 d2, double (&t)[2 * kRS]) {
+#pragma unroll
+  for (int r = 0; r < 2 * kRS; ++r) t[r] = 0.0;
+  constexpr int W = (L / 2) / 2 + 4;
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    const double2 av = a2(w), dv = d2(w);
+#pragma unroll
+    for (int pp = 0; pp < kRS; ++pp) {
+      const int qy = pp - 7 + 2 * w;
+      const int qx = qy + 1;
+      if (qy >= 0 && qy < L / 2) {
+        t[2 * pp] = fma(av.y, taps.lo[2 * qy], t[2 * pp]);
+        t[2 * pp] = fma(dv.y, taps.hi[2 * qy], t[2 * pp]);
+        t[2 * pp + 1] = fma(av.y, taps.lo[2 * qy + 1], t[2 * pp + 1]);
+        t[2 * pp + 1] = fma(dv.y, taps.hi[2 * qy + 1], t[2 * pp + 1]);
+      }
+      if (qx >= 0 && qx < L / 2) {
+        t[2 * pp] = fma(av.x, taps.lo[2 * qx], t[2 * pp]);
+        t[2 * pp] = fma(dv.x, taps.hi[2 * qx], t[2 * pp]);
+        t[2 * pp + 1] = fma(av.x, taps.lo[2 * qx + 1], t[2 * pp + 1]);
+        t[2 * pp + 1] = fma(dv.x, taps.hi[2 * qx + 1], t[2 * pp + 1]);
+      }
+    }
+  }
+}
+
+template <int L, bool RESIDENT>
+__global__ void __launch_bounds__(kThreads)
+k_wpt_rev(const __grid_constant__ Taps taps, const __grid_constant__ WptRevArgs a) {
+  extern __shared__ double2 smem2[];
+  const int tid = threadIdx.x;
+  const int m = a.m, h0 = a.h0;
+
+  if constexpr (!RESIDENT) {
+    // ---------------- tile mode ----------------
+    const int64_t line = blockIdx.x / a.tiles_per_line;
+    const int tile = int(blockIdx.x % a.tiles_per_line);
+    const int T = a.T;
+    const int t0 = tile * T;
+    double2* cur = smem2;
+    double2* nxt = smem2 + a.buf_cap;
+    {
+      // stage all 2^m leaf packets: local sample i of node j is slot O + i (periodic) of packet j
+      const int wm = h0 >> m;
+      const int O = (t0 >> m) - a.F[m] - a.ru8;
+      const int per_node = a.len[m] / 2;
+      const double* src = a.src + line * a.src_os;
+      const int total = per_node << m;
+      for (int it = tid; it < total; it += kThreads) {
+        const int node = it / per_node, j2 = it - node * per_node;
+        cp_async16(&cur[node * a.cap[m] + pad2(j2)], src + int64_t(node) * wm + ((O + 2 * j2) & (wm - 1)));
+      }
+      cp_async_wait_all();
+      __syncthreads();
+    }
+    for (int k = m; k >= 1; --k) {
+      const int groups = ((T >> k) + a.F[k]) / kRS;      // per parent node
+      const int base0 = 5 * a.g0[k];
+      const int cap_in = a.cap[k], cap_out = a.cap[k - 1];
+      const int items = groups << (k - 1);
+      for (int it = tid; it < items; it += kThreads) {
+        const int par = it / groups, g = it - par * groups;
+        const double2* A = cur + (2 * par) * cap_in + base0 + 5 * g;   // pad2(4g'+3-w) = 5g' + (3-w) + floor((3-w)/4)
+        const double2* D = A + cap_in;
+        double t[2 * kRS];
+        rev_step8<L>(taps, [&](int w) { return A[(3 - w) + ((3 - w) >> 2)]; },
+                     [&](int w) { return D[(3 - w) + ((3 - w) >> 2)]; }, t);
+        if (k > 1) {
+          double2* Y = nxt + par * cap_out;
+#pragma unroll
+          for (int e = 0; e < kRS; ++e) Y[pad2(kRS * g + e)] = make_double2(t[2 * e], t[2 * e + 1]);
+        } else {
+          double* y = a.dst + line * a.dst_os + t0 + 2 * kRS * g;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) st_global_v4(y + 4 * e, t[4 * e], t[4 * e + 1], t[4 * e + 2], t[4 * e + 3]);
+        }
+      }
+      __syncthreads();
+      double2* tmp = cur; cur = nxt; nxt = tmp;
+    }
+  } else {
+    // ---------------- resident mode ----------------
+    const int G = a.G;
+    const int64_t line0 = int64_t(blockIdx.x) * G;
+    const int nlines = int(min(int64_t(G), a.lines - line0));
+    const int cap = a.buf_cap;
+    double2* cur = smem2;
+    double2* nxt = smem2 + size_t(G) * cap;
+    {
+      const int per_line = h0 >> 1;
+      for (int it = tid; it < nlines * per_line; it += kThreads) {
+        const int ln = it / per_line, k2 = it - ln * per_line;
+        cp_async16(&cur[ln * cap + pad2(k2)], a.src + (line0 + ln) * a.src_os + 2 * k2);
+      }
+      cp_async_wait_all();
+      __syncthreads();
+    }
+    for (int k = m; k >= 1; --k) {
+      const int half = h0 >> k;      // width of every node at level k
+      const bool last = (k == 1);
+      if (half >= kRS) {
+        const int gpp = half / kRS;                 // groups per parent
+        const int per_line = gpp << (k - 1);        // == h0 / 16
+        const int mask2 = (half >> 1) - 1;
+        for (int it = tid; it < nlines * per_line; it += kThreads) {
+          const int ln = it / per_line, r = it - ln * per_line;
+          const int par = r / gpp, g = r - par * gpp;
+          const double2* cl = cur + ln * cap;
+          const int offA = (2 * par) * (half >> 1), offD = offA + (half >> 1);
+          const int c = 4 * g + 3;
+          double t[2 * kRS];
+          rev_step8<L>(taps, [&](int w) { return cl[pad2(offA + ((c - w) & mask2))]; },
+                       [&](int w) { return cl[pad2(offD + ((c - w) & mask2))]; }, t);
+          if (!last) {
+            double2* y = nxt + ln * cap;
+            const int o = par * half + kRS * g;     // parent starts at sample par * 2 * half
+#pragma unroll
+            for (int e = 0; e < kRS; ++e) y[pad2(o + e)] = make_double2(t[2 * e], t[2 * e + 1]);
+          } else {
+            double* y = a.dst + (line0 + ln) * a.dst_os + 2 * kRS * g;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) st_global_v4(y + 4 * e, t[4 * e], t[4 * e + 1], t[4 * e + 2], t[4 * e + 3]);
+          }
+        }
+      } else {
+        // nodes of 1, 2 or 4 coefficients: one thread per (line, parent, slot), true modular wrap
+        const int per_line = half << (k - 1);       // == h0 / 2
+        const int mask = half - 1;
+        for (int it = tid; it < nlines * per_line; it += kThreads) {
+          const int ln = it / per_line, r = it - ln * per_line;
+          const int par = r / half, p = r - par * half;
+          const double2* cl = cur + ln * cap;
+          const int offA = (2 * par) * half, offD = offA + half;
+          double t0v = 0.0, t1v = 0.0;
+#pragma unroll
+          for (int q = 0; q < L / 2; ++q) {
+            const int i = (p - q) & mask;
+            const double av = sm_scalar(cl, offA + i), dv = sm_scalar(cl, offD + i);
+            t0v = fma(av, taps.lo[2 * q], t0v);
+            t0v = fma(dv, taps.hi[2 * q], t0v);
+            t1v = fma(av, taps.lo[2 * q + 1], t1v);
+            t1v = fma(dv, taps.hi[2 * q + 1], t1v);
+          }
+          if (!last) {
+            nxt[ln * cap + pad2(par * half + p)] = make_double2(t0v, t1v);
+          } else {
+            double* y = a.dst + (line0 + ln) * a.dst_os + 2 * p;
+            y[0] = t0v;
+            y[1] = t1v;
+          }
+        }
+      }
+      __syncthreads();
+      double2* tmp = cur; cur = nxt; nxt = tmp;
+    }
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+
+static int round_up8(int v) { return (v + 7) & ~7; }
+
+// Fills the per-level geometry of a tile-mode launch and returns its shared memory (bytes).
+static size_t wpt_rev_tile_geometry(int L, WptRevArgs& a) {
+  a.ru8 = round_up8(L / 2 - 1);
+  int N = 0;
+  for (int k = 1; k <= a.m; ++k) {
+    a.F[k] = round_up8((N + 1) / 2);
+    N = a.F[k] + L / 2 - 1;
+  }
+  a.F[a.m + 1] = 0;
+  int cap = 0;
+  for (int k = 1; k <= a.m; ++k) {
+    a.len[k] = (k == a.m) ? (a.T >> k) + a.F[k] + a.ru8 : (a.T >> k) + 2 * a.F[k + 1];
+    a.g0[k] = (k == a.m) ? a.ru8 / kRS : (2 * a.F[k + 1] - a.F[k]) / kRS;
+    a.cap[k] = pad2_size(a.len[k] / 2);
+    const int c = (1 << k) * a.cap[k];
+    if (c > cap) cap = c;
+  }
+  a.cap[0] = 0;
+  a.buf_cap = cap;
+  return size_t(2) * cap * sizeof(double2);
+}
+
+int wpt_rev_tile_levels(int L, int T, int want, size_t smem_limit) {
+  WptRevArgs a;
+  a.T = T;
+  int m = 1;
+  while (m < want && m < kMaxFuse && (T >> (m + 1)) >= kRS) {
+    a.m = m + 1;
+    if (wpt_rev_tile_geometry(L, a) > smem_limit) break;
+    ++m;
+  }
+  return m;
+}
+
+template <int L>
+static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, WptRevArgs a, bool resident) {
+  size_t smem;
+  int64_t grid;
+  if (!resident) {
+    if (a.m < 1 || a.m > kMaxFuse || (a.T >> a.m) < kRS) return cudaErrorInvalidValue;
+    smem = wpt_rev_tile_geometry(L, a);
+    a.tiles_per_line = a.h0 / a.T;
+    grid = a.lines * a.tiles_per_line;
+  } else {
+    a.buf_cap = pad2_size(max(1, a.h0 / 2));
+    smem = size_t(2) * a.G * a.buf_cap * sizeof(double2);
+    grid = (a.lines + a.G - 1) / a.G;
+  }
+  if (grid > 0x7fffffff) return cudaErrorInvalidConfiguration;
+  auto kern = resident ? k_wpt_rev<L, true> : k_wpt_rev<L, false>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return e;
+  }
+  kern<<<int(grid), kThreads, smem, ctx->stream>>>(taps, a);
+  ctx->launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_wpt_rev(jwc_ctx* ctx, int L, const Taps& taps, const WptRevArgs& a, bool resident) {
+  switch (L) {
+#define JWC_CASE(LL) case LL: return launch_L<LL>(ctx, taps, a, resident);
+    JWC_FOR_EACH_L(JWC_CASE)
+#undef JWC_CASE
+  }
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace jwc
