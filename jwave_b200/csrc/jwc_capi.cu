@@ -90,6 +90,8 @@ extern "C" int jwc_create(jwc_ctx** out, int device) {
     get("rev_m", &ctx->rev_m);
     get("res_cap", &ctx->res_cap);
     get("wpt_tile", &ctx->wpt_tile);
+    get("wpt_m", &ctx->wpt_m);
+    get("wpt_threads", &ctx->wpt_threads);
   }
   *out = ctx;
   return JWC_OK;

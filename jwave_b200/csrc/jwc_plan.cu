@@ -255,7 +255,7 @@ static cudaError_t wpt_forward(jwc_ctx* ctx, const WaveletRec& w, const double* 
     Pass p;
     p.h = h;
     p.resident = (h <= ctx->res_cap);
-    p.m = p.resident ? left : wpt_tile_levels(w.L, ctx->wpt_tile, left, kWptSmemLimit);
+    p.m = p.resident ? left : wpt_tile_levels(w.L, ctx->wpt_tile, left < ctx->wpt_m ? left : ctx->wpt_m, kWptSmemLimit);
     passes[npass++] = p;
     h >>= p.m; left -= p.m;
   }
@@ -280,25 +280,28 @@ static cudaError_t wpt_forward(jwc_ctx* ctx, const WaveletRec& w, const double* 
 static cudaError_t wpt_reverse(jwc_ctx* ctx, const WaveletRec& w, const double* in, double* out,
                                int64_t outer, int n, int64_t inner, int level) {
   if (!fused_ok(ctx, in, out, n, inner) || n < 8) return wpt_reverse_generic(ctx, w, in, out, outer, n, inner, level);
-  // output widths of the passes: the first (resident) pass rebuilds packets up to res_cap, tile
-  // passes take it from there
+  // Output widths of the passes, chosen backwards from n: each tile pass rebuilds as many levels
+  // as its shared memory allows; whatever is left below res_cap is one resident pass.
   struct Pass { int h0, m; bool resident; };
   Pass passes[32];
   int npass = 0;
-  for (int cur = n >> level; cur < n;) {
+  const int cur0 = n >> level;
+  int widths[32];
+  int nw = 0;
+  for (int wv = n; wv > cur0;) {
+    widths[nw++] = wv;
+    if (wv <= ctx->res_cap) break;  // produced by the resident pass
+    int want = 0;
+    while ((cur0 << want) < wv) ++want;
+    if (want > ctx->wpt_m) want = ctx->wpt_m;
+    wv >>= wpt_rev_tile_levels(w.L, ctx->wpt_tile, want, kWptSmemLimit);
+  }
+  for (int i = nw - 1, cur = cur0; i >= 0; --i) {
     Pass p;
-    if (2 * cur <= ctx->res_cap) {
-      p.h0 = n < ctx->res_cap ? n : ctx->res_cap;
-      p.resident = true;
-      p.m = 0;
-      while ((cur << p.m) < p.h0) ++p.m;
-    } else {
-      int want = 0;
-      while ((cur << want) < n) ++want;
-      p.m = wpt_rev_tile_levels(w.L, ctx->wpt_tile, want, kWptSmemLimit);
-      p.h0 = cur << p.m;
-      p.resident = false;
-    }
+    p.h0 = widths[i];
+    p.resident = (p.h0 <= ctx->res_cap);
+    p.m = 0;
+    while ((cur << p.m) < p.h0) ++p.m;
     passes[npass++] = p;
     cur = p.h0;
   }

@@ -23,10 +23,10 @@
 namespace jwc {
 
 template <int L, bool RESIDENT>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(512)
 k_wpt_fwd(const __grid_constant__ Taps taps, const WptFwdArgs a) {
   extern __shared__ double2 smem2[];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, nthr = blockDim.x;
   const int m = a.m, h = a.h;
 
   if constexpr (!RESIDENT) {
@@ -39,7 +39,7 @@ k_wpt_fwd(const __grid_constant__ Taps taps, const WptFwdArgs a) {
     double2* nxt = smem2 + a.buf_cap;
     const double* src = a.src + line * a.src_os;
     const int base = tile * T;
-    for (int k2 = tid; k2 < n0 / 2; k2 += kThreads)
+    for (int k2 = tid; k2 < n0 / 2; k2 += nthr)
       cp_async16(&cur[pad2(k2)], src + ((base + 2 * k2) & (h - 1)));
     cp_async_wait_all();
     __syncthreads();
@@ -53,7 +53,7 @@ k_wpt_fwd(const __grid_constant__ Taps taps, const WptFwdArgs a) {
       const int cap_out = pad2_size(n_out / 2 + 4);
       const int items = groups << (k - 1);                          // nodes_in * groups
       const bool last = (k == m);
-      for (int it = tid; it < items; it += kThreads) {
+      for (int it = tid; it < items; it += nthr) {
         const int node = it / groups, g = it - node * groups;
         const double2* w = cur + node * cap_in + 5 * g;             // pad2(4g + q) == 5g + q + (q >> 2)
         double lo[kR], hi[kR];
@@ -85,7 +85,7 @@ k_wpt_fwd(const __grid_constant__ Taps taps, const WptFwdArgs a) {
     double2* nxt = smem2 + size_t(G) * cap;
     {
       const int per_line = h >> 1;
-      for (int it = tid; it < nlines * per_line; it += kThreads) {
+      for (int it = tid; it < nlines * per_line; it += nthr) {
         const int ln = it / per_line, k2 = it - ln * per_line;
         cp_async16(&cur[ln * cap + pad2(k2)], a.src + (line0 + ln) * a.src_os + 2 * k2);
       }
@@ -100,7 +100,7 @@ k_wpt_fwd(const __grid_constant__ Taps taps, const WptFwdArgs a) {
         const int gpn = h_out / kR;                        // groups per node (power of two)
         const int per_line = gpn << lg_nodes;              // == h / 8
         const int mask2 = (h_in >> 1) - 1;
-        for (int it = tid; it < nlines * per_line; it += kThreads) {
+        for (int it = tid; it < nlines * per_line; it += nthr) {
           const int ln = it / per_line, r = it - ln * per_line;
           const int node = r / gpn, g = r - node * gpn;
           const double2* cl = cur + ln * cap;
@@ -123,7 +123,7 @@ k_wpt_fwd(const __grid_constant__ Taps taps, const WptFwdArgs a) {
       } else {
         // nodes of 2 or 4 samples in, 1 or 2 out: one thread per (line, node, i); true modular wrap
         const int per_line = h_out << lg_nodes;            // == h / 2
-        for (int it = tid; it < nlines * per_line; it += kThreads) {
+        for (int it = tid; it < nlines * per_line; it += nthr) {
           const int ln = it / per_line, r = it - ln * per_line;
           const int node = r / h_out, i = r - node * h_out;
           const double2* cl = cur + ln * cap;
@@ -197,7 +197,7 @@ static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, WptFwdArgs a, bool r
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
   }
-  kern<<<int(grid), kThreads, smem, ctx->stream>>>(taps, a);
+  kern<<<int(grid), ctx->wpt_threads, smem, ctx->stream>>>(taps, a);
   ctx->launches++;
   return cudaGetLastError();
 }

@@ -50,10 +50,10 @@ __device__ __forceinline__ void rev_step8(const Taps& taps, A2 a2, D2 d2, double
 }
 
 template <int L, bool RESIDENT>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(512)
 k_wpt_rev(const __grid_constant__ Taps taps, const __grid_constant__ WptRevArgs a) {
   extern __shared__ double2 smem2[];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, nthr = blockDim.x;
   const int m = a.m, h0 = a.h0;
 
   if constexpr (!RESIDENT) {
@@ -71,7 +71,7 @@ k_wpt_rev(const __grid_constant__ Taps taps, const __grid_constant__ WptRevArgs 
       const int per_node = a.len[m] / 2;
       const double* src = a.src + line * a.src_os;
       const int total = per_node << m;
-      for (int it = tid; it < total; it += kThreads) {
+      for (int it = tid; it < total; it += nthr) {
         const int node = it / per_node, j2 = it - node * per_node;
         cp_async16(&cur[node * a.cap[m] + pad2(j2)], src + int64_t(node) * wm + ((O + 2 * j2) & (wm - 1)));
       }
@@ -83,7 +83,7 @@ k_wpt_rev(const __grid_constant__ Taps taps, const __grid_constant__ WptRevArgs 
       const int base0 = 5 * a.g0[k];
       const int cap_in = a.cap[k], cap_out = a.cap[k - 1];
       const int items = groups << (k - 1);
-      for (int it = tid; it < items; it += kThreads) {
+      for (int it = tid; it < items; it += nthr) {
         const int par = it / groups, g = it - par * groups;
         const double2* A = cur + (2 * par) * cap_in + base0 + 5 * g;   // pad2(4g'+3-w) = 5g' + (3-w) + floor((3-w)/4)
         const double2* D = A + cap_in;
@@ -113,7 +113,7 @@ k_wpt_rev(const __grid_constant__ Taps taps, const __grid_constant__ WptRevArgs 
     double2* nxt = smem2 + size_t(G) * cap;
     {
       const int per_line = h0 >> 1;
-      for (int it = tid; it < nlines * per_line; it += kThreads) {
+      for (int it = tid; it < nlines * per_line; it += nthr) {
         const int ln = it / per_line, k2 = it - ln * per_line;
         cp_async16(&cur[ln * cap + pad2(k2)], a.src + (line0 + ln) * a.src_os + 2 * k2);
       }
@@ -127,7 +127,7 @@ k_wpt_rev(const __grid_constant__ Taps taps, const __grid_constant__ WptRevArgs 
         const int gpp = half / kRS;                 // groups per parent
         const int per_line = gpp << (k - 1);        // == h0 / 16
         const int mask2 = (half >> 1) - 1;
-        for (int it = tid; it < nlines * per_line; it += kThreads) {
+        for (int it = tid; it < nlines * per_line; it += nthr) {
           const int ln = it / per_line, r = it - ln * per_line;
           const int par = r / gpp, g = r - par * gpp;
           const double2* cl = cur + ln * cap;
@@ -151,7 +151,7 @@ k_wpt_rev(const __grid_constant__ Taps taps, const __grid_constant__ WptRevArgs 
         // nodes of 1, 2 or 4 coefficients: one thread per (line, parent, slot), true modular wrap
         const int per_line = half << (k - 1);       // == h0 / 2
         const int mask = half - 1;
-        for (int it = tid; it < nlines * per_line; it += kThreads) {
+        for (int it = tid; it < nlines * per_line; it += nthr) {
           const int ln = it / per_line, r = it - ln * per_line;
           const int par = r / half, p = r - par * half;
           const double2* cl = cur + ln * cap;
@@ -239,7 +239,7 @@ static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, WptRevArgs a, bool r
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
   }
-  kern<<<int(grid), kThreads, smem, ctx->stream>>>(taps, a);
+  kern<<<int(grid), ctx->wpt_threads, smem, ctx->stream>>>(taps, a);
   ctx->launches++;
   return cudaGetLastError();
 }
