@@ -33,11 +33,16 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (wavelet class, kind, n, level, signals per GPU, description)
+    # name: (wavelet class, kind, n, level, items per GPU, description)
     "c2": ("Daubechies4", "fwt", 1 << 14, 14, 65536,
            "Daubechies4 FWT 1-D full depth (14 levels), 65536 signals x 2^14 fp64 per GPU"),
     "c3": ("Symlet8", "wpt", 1 << 16, 6, 4096,
            "Symlet8 WPT 1-D 6 levels, 4096 signals x 2^16 fp64 per GPU"),
+    # 2-D / 3-D configs (device-resident timing only; `n` is the edge length, level = log2 n per axis)
+    "c4": ("Daubechies20", "fwt2d", 8192, 13, 16,
+           "Daubechies20 FWT 2-D full depth, 8192 x 8192 fp64 images, 16 per GPU per step (BASELINE batch: 64)"),
+    "c5": ("Coiflet5", "fwt3d", 1024, 10, 1,
+           "Coiflet5 FWT 3-D full depth on one 1024^3 fp64 volume per GPU (single-GPU form of config 5)"),
 }
 METRIC = "Daub4 FWT / Sym8 WPT GSamples/s at 1-8 B200, % HBM roofline, vs JWave CPU"
 FP64_PEAK_TFLOPS = 36.7  # measured here with tools/microbench.cu (DFMA), see DESIGN.md
@@ -201,20 +206,40 @@ def main():
     cls, kind, n, level, batch, desc = WORKLOADS[args.workload]
     if args.batch:
         batch = args.batch
-    K = _lib.FWT if kind == "fwt" else _lib.WPT
+    dims = {"fwt": 1, "wpt": 1, "fwt2d": 2, "fwt3d": 3}[kind]
+    K = _lib.WPT if kind == "wpt" else _lib.FWT
     wavelet = jw.WaveletBuilder.create(cls)
     L = wavelet.getMotherWavelength()
     dev = DeviceTransforms(wavelet, local)
 
     gen = torch.Generator(device="cuda")
     gen.manual_seed(42 + rank)
-    x = torch.randn(batch, n, dtype=torch.float64, device="cuda", generator=gen)
+    slab = None
+    shape = {1: (batch, n), 2: (batch, n, n), 3: (n, n, n)}[dims]
+    if dims == 3 and world > 1:
+        # config 5 proper: ONE volume, slab-decomposed along i, all-to-all for the i pass
+        from jwave_b200.distributed import SlabVolumeTransform, device_axis_fn
+        slab = SlabVolumeTransform(device_axis_fn(dev), kind=K)
+        shape = (n // world, n, n)
+    x = torch.randn(*shape, dtype=torch.float64, device="cuda", generator=gen)
     coef = torch.empty_like(x)
     back = torch.empty_like(x)
 
+    def run(direction, src, dst):
+        if slab is not None:
+            res = slab.forward(src, n, level, level, level) if direction == _lib.FORWARD else \
+                slab.reverse(src, n, level, level, level)
+            dst.copy_(res)
+        elif dims == 1:
+            dev.transform1d(K, direction, src, level, out=dst)
+        elif dims == 2:
+            dev.transform2d(K, direction, src, level, level, out=dst)
+        else:
+            dev.transform3d(K, direction, src, level, level, level, out=dst)
+
     def step():
-        dev.transform1d(K, _lib.FORWARD, x, level, out=coef)
-        dev.transform1d(K, _lib.REVERSE, coef, level, out=back)
+        run(_lib.FORWARD, x, coef)
+        run(_lib.REVERSE, coef, back)
 
     def barrier():
         if world > 1:
@@ -237,9 +262,9 @@ def main():
     ev[0].record()
     for i in range(args.steps):
         fwd_ev[i][0].record()
-        dev.transform1d(K, _lib.FORWARD, x, level, out=coef)
+        run(_lib.FORWARD, x, coef)
         fwd_ev[i][1].record()
-        dev.transform1d(K, _lib.REVERSE, coef, level, out=back)
+        run(_lib.REVERSE, coef, back)
     ev[1].record()
     barrier()
     clocks = sampler.stop() if sampler else None
@@ -252,13 +277,13 @@ def main():
     ms, fwd_ms = float(t[0]), float(t[1])
     ms_per_step = ms / args.steps
     rev_ms = ms_per_step - fwd_ms
-    samples = batch * n
+    samples = x.numel()  # per GPU
     value = 2.0 * samples * world / (ms_per_step * 1e-3) * 1e-9
 
     # ---- roofline of the dominant kernel (forward pass) ---------------------------------------
     hbm_peak, peak_src = peaks()
-    bytes_per_sample = 16.0  # one read + one write of every sample
-    flops_per_sample = (2.0 * L * 2.0 * (1.0 - 0.5 ** level)) if kind == "fwt" else 2.0 * L * level
+    bytes_per_sample = 16.0 * dims  # one read + one write of every sample per axis pass
+    flops_per_sample = 2.0 * L * level if kind == "wpt" else dims * (2.0 * L * 2.0 * (1.0 - 0.5 ** level))
     t_hbm = samples * bytes_per_sample / (hbm_peak * 1e9)
     t_fp64 = samples * flops_per_sample / (FP64_PEAK_TFLOPS * 1e12)
     if t_hbm >= t_fp64:
@@ -268,7 +293,7 @@ def main():
         achieved = samples * flops_per_sample / (fwd_ms * 1e-3) * 1e-12
         roof = {"bound": "fp64", "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
                 "frac": achieved / FP64_PEAK_TFLOPS}
-    roof.update({"traffic": None, "kernel": f"forward pass ({'k_fwt_fwd' if kind == 'fwt' else 'k_wpt_fwd'}<{L}>, all launches)",
+    roof.update({"traffic": None, "kernel": f"forward pass ({'k_wpt_fwd' if kind == 'wpt' else 'k_fwt_fwd'}<{L}>, all launches)",
                  "peak_source": peak_src if roof["bound"] == "hbm" else "measured DFMA peak (tools/microbench.cu)",
                  "forward_ms": fwd_ms, "reverse_ms": rev_ms,
                  "algorithmic_bytes_per_sample": bytes_per_sample, "algorithmic_flops_per_sample": flops_per_sample,
@@ -277,7 +302,7 @@ def main():
 
     # ---- e2e: the same step through the host-buffer C ABI ------------------------------------
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and dims == 1:
         eb = batch if world == 1 else max(batch // world, 1)
         host = jw.CudaFastWaveletTransform(wavelet, context=dev.ctx) if kind == "fwt" else \
             jw.CudaWaveletPacketTransform(wavelet, context=dev.ctx)
@@ -312,16 +337,18 @@ def main():
         del hx, hc, hb
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and dims == 1:
         cpu = cpu_sample(cls, kind, n, level)
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "GSamples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong" if slab is not None else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "step": "forward + reverse of the whole batch",
-                       "signals_per_gpu": batch, "n": n, "level": level, "wavelet": cls, "taps": L,
+            "config": {"workload": desc + (f"; one volume slab-decomposed over {world} GPUs, 2 all-to-all per direction"
+                                           if slab is not None else ""), "step": "forward + reverse of the whole batch",
+                       "items_per_gpu": batch, "shape": list(shape), "n": n, "level": level, "wavelet": cls, "taps": L,
                        "parallelism": f"signals sharded over {world} GPU(s), no collective",
                        "l2": f"inputs ({samples * 8 / 2**30:.1f} GiB per array) exceed the 126 MB L2; no flush needed"},
             "forward_gsps": samples * world / (fwd_ms * 1e-3) * 1e-9,

@@ -91,6 +91,10 @@ extern "C" int jwc_create(jwc_ctx** out, int device) {
     get("res_cap", &ctx->res_cap);
     get("wpt_tile", &ctx->wpt_tile);
     get("wpt_m", &ctx->wpt_m);
+    get("str_tile", &ctx->str_tile);
+    get("str_rev_tile", &ctx->str_rev_tile);
+    get("str_rev_m", &ctx->str_rev_m);
+    get("str_cap", &ctx->str_cap);
     get("wpt_threads", &ctx->wpt_threads);
   }
   *out = ctx;

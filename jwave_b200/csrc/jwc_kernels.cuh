@@ -39,6 +39,30 @@ struct FwtRevArgs {
 };
 cudaError_t launch_fwt_rev(jwc_ctx* ctx, int L, const Taps& taps, const FwtRevArgs& a, bool resident);
 
+// ---- FWT along a strided axis (jwc_fwt_strided.cu) ------------------------------------------------
+struct FwtFwdStrArgs {
+  const double* src; int64_t src_os;    // element (o, s, c) at src + o * src_os + s * inner + c
+  double* dstD; int64_t dstD_os;        // final output: d_k at rows (h >> k) ...
+  double* dstA; int64_t dstA_os;        // a_m destination
+  int64_t outer, inner;
+  int h, m, T;
+  int tiles_per_line, cblocks, rows0, rows1;  // filled in by the launcher
+};
+int fwt_str_tile_levels(int L, int T);
+cudaError_t launch_fwt_fwd_str(jwc_ctx* ctx, int L, const Taps& taps, const FwtFwdStrArgs& a, bool resident);
+
+struct FwtRevStrArgs {
+  const double* srcA; int64_t srcA_os;
+  const double* srcD; int64_t srcD_os;
+  double* dst; int64_t dst_os;
+  int64_t outer, inner;
+  int h0, m, T;
+  // filled in by the launcher
+  int tiles_per_line, cblocks, ru, rowsC, rowsP[2];
+  int F[kMaxFuse + 2], s0[kMaxFuse + 1], len[kMaxFuse + 1], offD[kMaxFuse + 1], offA[2];
+};
+cudaError_t launch_fwt_rev_str(jwc_ctx* ctx, int L, const Taps& taps, const FwtRevStrArgs& a, bool resident);
+
 // ---- forward WPT, contiguous lines (jwc_wpt_fwd.cu) -----------------------------------------
 struct WptFwdArgs {
   const double* src; int64_t src_os;    // input lines (packets of width h)

@@ -78,10 +78,96 @@ static cudaError_t fwt_forward_generic(jwc_ctx* ctx, const WaveletRec& w, const 
   return cudaSuccess;
 }
 
+// Strided axis (inner > 1): the same pass structure with the [sample][8 columns] kernels.
+static bool strided_ok(const jwc_ctx* ctx, const double* in, const double* out, int n, int64_t inner) {
+  return !ctx->force_generic && inner >= 8 && inner % 8 == 0 && n >= 4 && aligned32(in) && aligned32(out);
+}
+
+static cudaError_t fwt_forward_strided(jwc_ctx* ctx, const WaveletRec& w, const double* in, double* out,
+                                       int64_t outer, int n, int64_t inner, int level) {
+  const int cap = ctx->str_cap, tileT = ctx->str_tile;
+  const int m_tile = fwt_str_tile_levels(w.L, tileT);
+  double* S[2] = {nullptr, nullptr};
+  if (n > cap && level > m_tile) {
+    JWC_TRY(ensure_scratch(ctx, 1, size_t(outer) * (n >> m_tile) * inner * sizeof(double), &S[1]));
+    if ((n >> m_tile) > cap && level > 2 * m_tile)
+      JWC_TRY(ensure_scratch(ctx, 0, size_t(outer) * (n >> (2 * m_tile)) * inner * sizeof(double), &S[0]));
+  }
+  FwtFwdStrArgs a;
+  a.src = in; a.src_os = int64_t(n) * inner;
+  a.dstD = out; a.dstD_os = int64_t(n) * inner;
+  a.outer = outer; a.inner = inner;
+  int h = n, left = level, pass = 0;
+  while (left > 0) {
+    const bool resident = (h <= cap) || (h < tileT);
+    a.h = h;
+    a.T = resident ? h : tileT;
+    a.m = resident ? left : (left < m_tile ? left : m_tile);
+    const bool last = (a.m == left);
+    a.dstA = last ? out : S[(pass + 1) & 1];
+    a.dstA_os = last ? int64_t(n) * inner : int64_t(h >> a.m) * inner;
+    JWC_TRY(launch_fwt_fwd_str(ctx, w.L, w.de, a, resident));
+    a.src = a.dstA; a.src_os = a.dstA_os;
+    h >>= a.m; left -= a.m; ++pass;
+  }
+  return cudaSuccess;
+}
+
+static cudaError_t fwt_reverse_strided(jwc_ctx* ctx, const WaveletRec& w, const double* in, double* out,
+                                       int64_t outer, int n, int64_t inner, int level) {
+  struct Pass { int h0, m; bool resident; };
+  Pass passes[32];
+  int npass = 0;
+  size_t need[2] = {0, 0};
+  const int cap = ctx->str_cap, tileT = ctx->str_rev_tile;
+  int rev_m = ctx->str_rev_m;
+  while ((tileT >> rev_m) < 4) --rev_m;
+  int widths[32];
+  int nw = 0;
+  const int cur0 = n >> level;
+  for (int wv = n; wv > cur0; wv >>= rev_m) {
+    widths[nw++] = wv;
+    if (wv <= cap || wv < tileT) break;  // produced by the resident pass
+    if ((wv >> rev_m) <= cur0) break;
+  }
+  for (int i = nw - 1, cur = cur0; i >= 0; --i) {
+    Pass p;
+    p.h0 = widths[i];
+    p.resident = (p.h0 <= cap) || (p.h0 < tileT);
+    p.m = 0;
+    while ((cur << p.m) < p.h0) ++p.m;
+    if (p.h0 < n) {
+      const size_t bytes = size_t(outer) * p.h0 * inner * sizeof(double);
+      if (bytes > need[npass & 1]) need[npass & 1] = bytes;
+    }
+    passes[npass++] = p;
+    cur = p.h0;
+  }
+  double* S[2] = {nullptr, nullptr};
+  for (int i = 0; i < 2; ++i)
+    if (need[i]) JWC_TRY(ensure_scratch(ctx, i, need[i], &S[i]));
+  FwtRevStrArgs a;
+  a.srcA = in; a.srcA_os = int64_t(n) * inner;
+  a.srcD = in; a.srcD_os = int64_t(n) * inner;
+  a.outer = outer; a.inner = inner;
+  for (int i = 0; i < npass; ++i) {
+    const Pass& p = passes[i];
+    const bool last = (p.h0 == n);
+    a.h0 = p.h0; a.m = p.m;
+    a.T = p.resident ? p.h0 : tileT;
+    a.dst = last ? out : S[i & 1];
+    a.dst_os = last ? int64_t(n) * inner : int64_t(p.h0) * inner;
+    JWC_TRY(launch_fwt_rev_str(ctx, w.L, w.re, a, p.resident));
+    a.srcA = a.dst; a.srcA_os = a.dst_os;
+  }
+  return cudaSuccess;
+}
+
 // Fused plan: tile passes of m levels each while the width exceeds res_cap, then one resident
 // launch for everything that is left.  a_m of a tile pass goes to a compact scratch buffer.
 static cudaError_t fwt_forward(jwc_ctx* ctx, const WaveletRec& w, const double* in, double* out,
                                int64_t outer, int n, int64_t inner, int level) {
+  if (inner > 1 && strided_ok(ctx, in, out, n, inner)) return fwt_forward_strided(ctx, w, in, out, outer, n, inner, level);
   if (!fused_ok(ctx, in, out, n, inner)) return fwt_forward_generic(ctx, w, in, out, outer, n, inner, level);
   const int cap = ctx->res_cap, tileT = ctx->fwd_tile;
   int m_tile = fwt_tile_levels(w.L, tileT);
@@ -143,6 +229,7 @@ static cudaError_t fwt_reverse_generic(jwc_ctx* ctx, const WaveletRec& w, const 
 // to rev_m levels each.  Intermediate approximations go to compact scratch lines.
 static cudaError_t fwt_reverse(jwc_ctx* ctx, const WaveletRec& w, const double* in, double* out,
                                int64_t outer, int n, int64_t inner, int level) {
+  if (inner > 1 && strided_ok(ctx, in, out, n, inner)) return fwt_reverse_strided(ctx, w, in, out, outer, n, inner, level);
   if (!fused_ok(ctx, in, out, n, inner)) return fwt_reverse_generic(ctx, w, in, out, outer, n, inner, level);
   struct Pass { int h0, m; bool resident; };
   Pass passes[32];

@@ -1,0 +1,105 @@
+"""Multi-GPU layer: one process per GPU, torch.distributed for the plumbing.
+
+Two ways the path spreads over the GPUs of a box:
+
+* independent signals / images (configs 2-4): `shard_range` splits the batch into contiguous
+  blocks, every rank transforms its own block, NO collective touches the data;
+* one large volume (config 5): `SlabVolumeTransform` keeps the volume slab-decomposed along the
+  outer index i.  The two inner axes (k, j) are transformed locally on the owned slices; the
+  outer axis needs every i for a given (j, k), so one all-to-all re-slabs the volume along j, the
+  i-pass runs locally, and a second all-to-all restores the i-slab layout - the layout
+  BasicTransform.forward(double[][][]) returns (BasicTransform.java:509-566), just distributed.
+
+The local compute is injected (`axis_fn`), so the exchange logic is testable on CPU ranks with
+the `gloo` backend; on GPUs it is DeviceTransforms.axis (libjwave_cuda.so) and the collective
+runs over NCCL / NVLink.
+"""
+import torch
+import torch.distributed as dist
+
+FORWARD, REVERSE = 0, 1
+FWT, WPT = 0, 1
+
+
+def shard_range(total, rank, world):
+    """Contiguous block [start, stop) of `total` independent items owned by `rank`."""
+    base, extra = divmod(total, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+class SlabVolumeTransform:
+    """3-D FWT / WPT of a P x Q x R volume held as i-slabs: rank g owns [g P/W, (g+1) P/W) x Q x R.
+
+    axis_fn(kind, direction, x, outer, n, inner, level) -> tensor like x: the 1-D transform along
+    the middle axis of the dense [outer][n][inner] view of x (jwc_axis_dev semantics).
+    """
+
+    def __init__(self, axis_fn, kind=FWT, group=None):
+        self.axis_fn = axis_fn
+        self.kind = kind
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    # -- exchanges ---------------------------------------------------------------------------------
+    def _to_j_slabs(self, x):
+        """[P/W][Q][R] on every rank -> [P][Q/W][R] on every rank (one all-to-all)."""
+        W = self.world
+        if W == 1:
+            return x
+        p, Q, R = x.shape
+        send = x.view(p, W, Q // W, R).permute(1, 0, 2, 3).contiguous()  # [dest][i][j_local][k]
+        recv = torch.empty_like(send)                                       # [src][i_of_src][j_local][k]
+        dist.all_to_all_single(recv, send, group=self.group)
+        return recv.view(W * p, Q // W, R)  # src-major order is i order
+
+    def _to_i_slabs(self, y):
+        """[P][Q/W][R] on every rank -> [P/W][Q][R] on every rank (one all-to-all)."""
+        W = self.world
+        if W == 1:
+            return y
+        P, q, R = y.shape
+        send = y.contiguous()               # chunk d = rows of rank d's i range
+        recv = torch.empty_like(send)       # [src][i_local][j_of_src][k]
+        dist.all_to_all_single(recv, send, group=self.group)
+        return recv.view(W, P // W, q, R).permute(1, 0, 2, 3).reshape(P // W, W * q, R)
+
+    # -- transforms --------------------------------------------------------------------------------
+    def _check(self, x, P):
+        if x.dim() != 3 or x.shape[0] * self.world != P:
+            raise ValueError("expected this rank's [P/W][Q][R] slab")
+        if x.shape[1] % self.world:
+            raise ValueError("Q must be divisible by the number of ranks")
+
+    def forward(self, slab, P, lvlP, lvlQ, lvlR):
+        """BasicTransform.java:509-566 with its level shift (F5): axis k gets lvlQ, axis j gets
+        lvlP, then axis i gets lvlR."""
+        self._check(slab, P)
+        p, Q, R = slab.shape
+        t = self.axis_fn(self.kind, FORWARD, slab, p * Q, R, 1, lvlQ)   # rows of every slice
+        t = self.axis_fn(self.kind, FORWARD, t, p, Q, R, lvlP)          # columns of every slice
+        y = self._to_j_slabs(t)
+        y = self.axis_fn(self.kind, FORWARD, y, 1, P, y.shape[1] * R, lvlR)
+        return self._to_i_slabs(y)
+
+    def reverse(self, slab, P, lvlP, lvlQ, lvlR):
+        """BasicTransform.java:602-659: 2-D reverse of every slice (columns, then rows), then axis i."""
+        self._check(slab, P)
+        p, Q, R = slab.shape
+        t = self.axis_fn(self.kind, REVERSE, slab, p, Q, R, lvlP)
+        t = self.axis_fn(self.kind, REVERSE, t, p * Q, R, 1, lvlQ)
+        y = self._to_j_slabs(t)
+        y = self.axis_fn(self.kind, REVERSE, y, 1, P, y.shape[1] * R, lvlR)
+        return self._to_i_slabs(y)
+
+    def exchange_bytes(self, slab):
+        """Bytes this rank sends per all-to-all (the NVLink term of the roofline)."""
+        return slab.numel() * slab.element_size() * (self.world - 1) // max(self.world, 1)
+
+
+def device_axis_fn(dev):
+    """axis_fn backed by libjwave_cuda.so through jwave_b200.device.DeviceTransforms."""
+    def fn(kind, direction, x, outer, n, inner, level):
+        return dev.axis(kind, direction, x, outer, n, inner, level)
+    return fn

@@ -116,12 +116,36 @@ def test_input_is_not_mutated_and_output_is_fresh():
 @pytest.mark.parametrize("cls", ["Haar1", "Daubechies4", "Daubechies20", "Coiflet5"])
 def test_2d_parity(kind, cls):
     t = make(kind, cls)
-    for rows, cols, lv in ((64, 64, None), (16, 128, (2, 5)), (256, 8, (8, 0)), (1, 32, (0, 5)), (128, 256, None)):
+    for rows, cols, lv in ((64, 64, None), (16, 128, (2, 5)), (256, 8, (8, 0)), (1, 32, (0, 5)), (128, 256, None),
+                           (2048, 32, None), (1024, 16, (3, 2))):
         m = rng_signal(rows * 3 + cols, rows, cols)
         args = () if lv is None else lv
         cf = co.transform_2d(okind(kind), co.FORWARD, cls, m, *args)
         close(t.forward(m, *args), cf, np.abs(m).max())
         close(t.reverse(cf, *args), co.transform_2d(okind(kind), co.REVERSE, cls, cf, *args), np.abs(cf).max())
+
+
+@pytest.mark.parametrize("cls", ["Daubechies4", "Daubechies20", "Coiflet5", "Haar1"])
+def test_strided_axis_tile_and_resident(cls):
+    """Columns long enough for the tiled strided kernels (rows > 512 -> tile passes + resident
+    tail) and short ones (resident only), full and partial depth, via the axis primitive."""
+    import torch
+    from jwave_b200.device import DeviceTransforms
+    dev = DeviceTransforms(jw.WaveletBuilder.create(cls))
+    for outer, n, inner, level in ((2, 4096, 16, 12), (1, 2048, 40, 5), (3, 512, 8, 9), (1, 8192, 8, 13), (2, 64, 24, 6)):
+        x = rng_signal(n + inner, outer, n, inner)
+        def columns(direction, arr):  # 1-D transform of every (outer, inner) line along axis 1
+            lines = np.ascontiguousarray(arr.transpose(0, 2, 1).reshape(-1, n))
+            res = co.batch_1d(co.FWT, direction, cls, lines, level)
+            return np.ascontiguousarray(res.reshape(outer, inner, n).transpose(0, 2, 1))
+        ref = columns(co.FORWARD, x)
+        xd = torch.from_numpy(x).cuda()
+        fd = dev.axis(_lib.FWT, _lib.FORWARD, xd, outer, n, inner, level)
+        close(fd.cpu().numpy(), ref, np.abs(x).max())
+        back = columns(co.REVERSE, ref)
+        rd = dev.axis(_lib.FWT, _lib.REVERSE, torch.from_numpy(ref).cuda(), outer, n, inner, level)
+        close(rd.cpu().numpy(), back, np.abs(ref).max())
+    dev.close()
 
 
 def test_2d_equals_row_by_row_composition():
@@ -146,7 +170,8 @@ def test_batched_2d_parity():
 @pytest.mark.parametrize("cls", ["Haar1", "Coiflet5", "Daubechies4"])
 def test_3d_parity(kind, cls):
     t = make(kind, cls)
-    for shape, lv in (((16, 16, 16), None), ((4, 8, 32), (3, 5, 2)), ((32, 4, 8), (1, 1, 1)), ((8, 8, 8), (0, 3, 0))):
+    for shape, lv in (((16, 16, 16), None), ((4, 8, 32), (3, 5, 2)), ((32, 4, 8), (1, 1, 1)), ((8, 8, 8), (0, 3, 0)),
+                      ((64, 32, 64), None), ((1024, 8, 8), (3, 3, 10))):
         s = rng_signal(sum(shape), *shape)
         args = () if lv is None else lv
         cf = co.transform_3d(okind(kind), co.FORWARD, cls, s, *args)
