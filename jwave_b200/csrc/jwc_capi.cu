@@ -88,6 +88,7 @@ extern "C" int jwc_create(jwc_ctx** out, int device) {
     get("fwd_m", &ctx->fwd_m);
     get("rev_tile", &ctx->rev_tile);
     get("rev_m", &ctx->rev_m);
+    get("rev_rs", &ctx->rev_rs);
     get("res_cap", &ctx->res_cap);
     get("wpt_tile", &ctx->wpt_tile);
     get("wpt_m", &ctx->wpt_m);

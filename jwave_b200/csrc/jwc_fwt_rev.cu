@@ -3,7 +3,7 @@
 // Replaces the level loop of FastWaveletTransform.reverse (FastWaveletTransform.java:143-149)
 // around Wavelet.reverse (Wavelet.java:277-303) for `m` consecutive levels per launch.  The
 // reference's scatter `t[(2i+j) mod h] += a[i] s[j] + d[i] w[j]` is evaluated as a gather
-// (jwc_fused.cuh: rev_step8), so no atomics and no zero-fill are needed.
+// (rev_step below), so no atomics and no zero-fill are needed.
 //
 // Launch-level numbering: level 0 is the output of the launch (width h0), level m its coarsest
 // input a_m (width h0 >> m); d_k (width h0 >> k) sits at `srcD + (h0 >> k)` in every line,
@@ -20,22 +20,21 @@
 
 namespace jwc {
 
-constexpr int kRS = 8;  // coefficient slots (=> 16 time samples) per thread and step
-
-// 8 consecutive slots p = 8g' .. 8g'+7 -> t[16]:  t[2pp+r] = sum_q a[p-q] lo[2q+r] + d[p-q] hi[2q+r].
-// `a2(w)` / `d2(w)` return double2 number (4g' + 3 - w) of the a / d arrays, w = 0 .. L/4 + 3.
-template <int L, class A2, class D2>
-__device__ __forceinline__ void rev_step8(const Taps& taps, A2 a2, D2 d2, double (&t)[2 * kRS]) {
+// RS consecutive slots p = RS g' .. RS g' + RS - 1 (RS = 8 or 4) -> t[2 RS]:
+//   t[2pp + r] = sum_q a[p - q] lo[2q + r] + d[p - q] hi[2q + r].
+// `a2(w)` / `d2(w)` return double2 number (RS/2 g' + RS/2 - 1 - w) of the a / d arrays, w = 0 .. L/4 + RS/2 - 1.
+template <int L, int RS, class A2, class D2>
+__device__ __forceinline__ void rev_step(const Taps& taps, A2 a2, D2 d2, double (&t)[2 * RS]) {
 #pragma unroll
-  for (int r = 0; r < 2 * kRS; ++r) t[r] = 0.0;
-  constexpr int W = (L / 2) / 2 + 4;
+  for (int r = 0; r < 2 * RS; ++r) t[r] = 0.0;
+  constexpr int W = (L / 2) / 2 + RS / 2;
 #pragma unroll
   for (int w = 0; w < W; ++w) {
     const double2 av = a2(w), dv = d2(w);
 #pragma unroll
-    for (int pp = 0; pp < kRS; ++pp) {
-      const int qy = pp - 7 + 2 * w;  // .y is slot 8g'+7-2w
-      const int qx = qy + 1;          // .x is slot 8g'+6-2w
+    for (int pp = 0; pp < RS; ++pp) {
+      const int qy = pp - (RS - 1) + 2 * w;  // .y is slot RS g' + RS - 1 - 2w
+      const int qx = qy + 1;                 // .x is the slot before it
       if (qy >= 0 && qy < L / 2) {
         t[2 * pp] = fma(av.y, taps.lo[2 * qy], t[2 * pp]);
         t[2 * pp] = fma(dv.y, taps.hi[2 * qy], t[2 * pp]);
@@ -52,7 +51,7 @@ __device__ __forceinline__ void rev_step8(const Taps& taps, A2 a2, D2 d2, double
   }
 }
 
-template <int L, bool RESIDENT>
+template <int L, bool RESIDENT, int kRS>
 __global__ void __launch_bounds__(kThreads)
 k_fwt_rev(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevArgs a) {
   extern __shared__ double2 smem2[];
@@ -92,17 +91,22 @@ k_fwt_rev(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevArgs 
       const int g0 = a.g0[k];
       for (int g = tid; g < groups; g += kThreads) {
         double t[2 * kRS];
-        // pad2(4g' + 3 - w) = 5g' + (3 - w) + floor((3 - w) / 4): a compile-time offset per w
-        const int base = 5 * (g + g0);
-        rev_step8<L>(taps, [&](int w) { return A[base + (3 - w) + ((3 - w) >> 2)]; },
-                     [&](int w) { return D[base + (3 - w) + ((3 - w) >> 2)]; }, t);
+        if constexpr (kRS == 8) {
+          // pad2(4g' + 3 - w) = 5g' + (3 - w) + floor((3 - w) / 4): a compile-time offset per w
+          const int base = 5 * (g + g0);
+          rev_step<L, 8>(taps, [&](int w) { return A[base + (3 - w) + ((3 - w) >> 2)]; },
+                         [&](int w) { return D[base + (3 - w) + ((3 - w) >> 2)]; }, t);
+        } else {
+          const int c = 4 * g0 + (kRS / 2) * g + kRS / 2 - 1;
+          rev_step<L, kRS>(taps, [&](int w) { return A[pad2(c - w)]; }, [&](int w) { return D[pad2(c - w)]; }, t);
+        }
         if (k > 1) {
 #pragma unroll
           for (int e = 0; e < kRS; ++e) Y[pad2(kRS * g + e)] = make_double2(t[2 * e], t[2 * e + 1]);
         } else {
           double* y = a.dst + line * a.dst_os + t0 + 2 * kRS * g;
 #pragma unroll
-          for (int e = 0; e < 4; ++e) st_global_v4(y + 4 * e, t[4 * e], t[4 * e + 1], t[4 * e + 2], t[4 * e + 3]);
+          for (int e = 0; e < kRS / 2; ++e) st_global_v4(y + 4 * e, t[4 * e], t[4 * e + 1], t[4 * e + 2], t[4 * e + 3]);
         }
       }
       __syncthreads();
@@ -137,9 +141,9 @@ k_fwt_rev(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevArgs 
           const int ln = it / gpl, g = it - ln * gpl;
           const double2* cl = C + ln * capC;
           const double2* al = from_c ? cl : P[k & 1] + ln * capP[k & 1];
-          const int c = 4 * g + 3;
+          const int c = (kRS / 2) * g + kRS / 2 - 1;
           double t[2 * kRS];
-          rev_step8<L>(taps, [&](int w) { return al[pad2((c - w) & mask2)]; },
+          rev_step<L, kRS>(taps, [&](int w) { return al[pad2((c - w) & mask2)]; },
                        [&](int w) { return cl[pad2(doff + ((c - w) & mask2))]; }, t);
           if (!last) {
             double2* y = P[(k - 1) & 1] + ln * capP[(k - 1) & 1];
@@ -148,7 +152,7 @@ k_fwt_rev(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevArgs 
           } else {
             double* y = a.dst + (line0 + ln) * a.dst_os + 2 * kRS * g;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) st_global_v4(y + 4 * e, t[4 * e], t[4 * e + 1], t[4 * e + 2], t[4 * e + 3]);
+            for (int e = 0; e < kRS / 2; ++e) st_global_v4(y + 4 * e, t[4 * e], t[4 * e + 1], t[4 * e + 2], t[4 * e + 3]);
           }
         }
       } else {
@@ -191,7 +195,7 @@ static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, FwtRevArgs a, bool r
   size_t smem;
   int grid;
   if (!resident) {
-    if (a.m < 1 || a.m > kMaxFuse || (a.T >> a.m) < kRS) return cudaErrorInvalidValue;
+    if (a.m < 1 || a.m > kMaxFuse || (a.T >> a.m) < 8) return cudaErrorInvalidValue;
     a.ru8 = round_up8(L / 2 - 1);
     int N = 0;  // N_{k-1}: left extension of a_{k-1} the level below needs
     for (int k = 1; k <= a.m; ++k) {
@@ -203,7 +207,7 @@ static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, FwtRevArgs a, bool r
     int capA[2] = {0, 0};
     for (int k = 1; k <= a.m; ++k) {
       a.len[k] = (k == a.m) ? (a.T >> k) + a.F[k] + a.ru8 : (a.T >> k) + 2 * a.F[k + 1];
-      a.g0[k] = (k == a.m) ? a.ru8 / kRS : (2 * a.F[k + 1] - a.F[k]) / kRS;
+      a.g0[k] = (k == a.m) ? a.ru8 / 8 : (2 * a.F[k + 1] - a.F[k]) / 8;
       a.offD[k] = off;
       off += pad2_size(a.len[k] / 2);
       if (pad2_size(a.len[k] / 2) > capA[k & 1]) capA[k & 1] = pad2_size(a.len[k] / 2);
@@ -222,7 +226,8 @@ static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, FwtRevArgs a, bool r
     smem = size_t(a.G) * (a.capC + a.capP[0] + a.capP[1]) * sizeof(double2);
     grid = int((a.lines + a.G - 1) / a.G);
   }
-  auto kern = resident ? k_fwt_rev<L, true> : k_fwt_rev<L, false>;
+  auto kern = resident ? (ctx->rev_rs == 4 ? k_fwt_rev<L, true, 4> : k_fwt_rev<L, true, 8>)
+                       : (ctx->rev_rs == 4 ? k_fwt_rev<L, false, 4> : k_fwt_rev<L, false, 8>);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;

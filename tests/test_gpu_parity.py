@@ -171,7 +171,7 @@ def test_batched_2d_parity():
 def test_3d_parity(kind, cls):
     t = make(kind, cls)
     for shape, lv in (((16, 16, 16), None), ((4, 8, 32), (3, 5, 2)), ((32, 4, 8), (1, 1, 1)), ((8, 8, 8), (0, 3, 0)),
-                      ((64, 32, 64), None), ((1024, 8, 8), (3, 3, 10))):
+                      ((64, 32, 64), (5, 6, 6)), ((1024, 8, 8), (3, 3, 10)), ((32, 32, 32), None)):
         s = rng_signal(sum(shape), *shape)
         args = () if lv is None else lv
         cf = co.transform_3d(okind(kind), co.FORWARD, cls, s, *args)
