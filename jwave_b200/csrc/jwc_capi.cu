@@ -86,9 +86,13 @@ extern "C" int jwc_create(jwc_ctx** out, int device) {
     };
     get("fwd_tile", &ctx->fwd_tile);
     get("fwd_m", &ctx->fwd_m);
+    get("fwd_r", &ctx->fwd_r);
     get("rev_tile", &ctx->rev_tile);
     get("rev_m", &ctx->rev_m);
     get("rev_rs", &ctx->rev_rs);
+    get("dbg", &ctx->dbg);
+    get("fwd_threads", &ctx->fwd_threads);
+    get("rev_threads", &ctx->rev_threads);
     get("res_cap", &ctx->res_cap);
     get("wpt_tile", &ctx->wpt_tile);
     get("wpt_m", &ctx->wpt_m);

@@ -39,6 +39,28 @@ __device__ __forceinline__ void ld_global_v4(const double* p, double& a, double&
   asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
 }
 
+// Forward step for R consecutive output pairs i = R g' .. R g' + R - 1: `win(q)` returns double2
+// number (R g' + q) of the input, q = 0 .. R + L/2 - 2 (same arithmetic as fwd_step4 below).
+template <int L, int R, class Win>
+__device__ __forceinline__ void fwd_stepR(const Taps& taps, Win win, double (&lo)[R], double (&hi)[R]) {
+#pragma unroll
+  for (int r = 0; r < R; ++r) lo[r] = hi[r] = 0.0;
+#pragma unroll
+  for (int q = 0; q < L / 2 + R - 1; ++q) {
+    const double2 v = win(q);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int jj = q - r;
+      if (jj >= 0 && jj < L / 2) {
+        lo[r] = fma(v.x, taps.lo[2 * jj], lo[r]);
+        hi[r] = fma(v.x, taps.hi[2 * jj], hi[r]);
+        lo[r] = fma(v.y, taps.lo[2 * jj + 1], lo[r]);
+        hi[r] = fma(v.y, taps.hi[2 * jj + 1], hi[r]);
+      }
+    }
+  }
+}
+
 // Forward step for 4 consecutive output pairs from a window held in shared memory.
 //   lo[r] = sum_j x[2(4g+r)+j] * taps.lo[j],  hi[r] likewise, j ascending (the reference's order,
 //   Wavelet.java:244-254, contracted to FMAs).

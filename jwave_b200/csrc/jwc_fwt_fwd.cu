@@ -16,11 +16,11 @@
 
 namespace jwc {
 
-template <int L, bool RESIDENT>
-__global__ void __launch_bounds__(kThreads)
+template <int L, bool RESIDENT, int R = 4>
+__global__ void __launch_bounds__(384)
 k_fwt_fwd(const __grid_constant__ Taps taps, const FwtFwdArgs a) {
   extern __shared__ double2 smem2[];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, nthr = blockDim.x;
 
   if constexpr (!RESIDENT) {
     // ---------------- tile mode ----------------
@@ -33,7 +33,7 @@ k_fwt_fwd(const __grid_constant__ Taps taps, const FwtFwdArgs a) {
     double2* nxt = smem2 + a.cap0;               // level k approximations
     const double* src = a.src + line * a.src_os;
     const int base = tile * T;
-    for (int k2 = tid; k2 < n0 / 2; k2 += kThreads)
+    for (int k2 = tid; k2 < n0 / 2; k2 += nthr)
       cp_async16(&cur[pad2(k2)], src + ((base + 2 * k2) & (h - 1)));   // periodic wrap of the halo
     cp_async_wait_all();
     __syncthreads();
@@ -42,21 +42,29 @@ k_fwt_fwd(const __grid_constant__ Taps taps, const FwtFwdArgs a) {
     for (int k = 1; k <= m; ++k) {
       const int n_det = T >> k;                                   // details this tile owns
       const int n_out = n_det + ((1 << (m - k)) - 1) * (L - 2);   // approximations incl. halo
-      const int groups = (n_out + kR - 1) / kR;
+      const int groups = (n_out + R - 1) / R;
       const bool last = (k == m);
       double* dD = outD + (h >> k) + tile * n_det;
       double* dA = a.dstA + line * a.dstA_os + tile * n_det;      // used when last
-      for (int g = tid; g < groups; g += kThreads) {
-        double lo[kR], hi[kR];
-        const double2* w = cur + pad2(kR * g);   // pad2(4g + q) == 5g + q + (q >> 2)
-        fwd_step4<L>(taps, [&](int q) { return w[q + (q >> 2)]; }, lo, hi);
-        if (!last) {
-          nxt[pad2(2 * g)] = make_double2(lo[0], lo[1]);
-          nxt[pad2(2 * g + 1)] = make_double2(lo[2], lo[3]);
+      for (int g = tid; g < groups; g += nthr) {
+        double lo[R], hi[R];
+        if constexpr (R == 4) {
+          const double2* w = cur + pad2(R * g);   // pad2(4g + q) == 5g + q + (q >> 2)
+          fwd_stepR<L, R>(taps, [&](int q) { return w[q + (q >> 2)]; }, lo, hi);
+          if (!last) {
+            nxt[pad2(2 * g)] = make_double2(lo[0], lo[1]);
+            nxt[pad2(2 * g + 1)] = make_double2(lo[2], lo[3]);
+          } else {
+            st_global_v4(dA + R * g, lo[0], lo[1], lo[2], lo[3]);
+          }
+          if (R * g < n_det) st_global_v4(dD + R * g, hi[0], hi[1], hi[2], hi[3]);
         } else {
-          st_global_v4(dA + kR * g, lo[0], lo[1], lo[2], lo[3]);
+          static_assert(R == 2 || R == 4, "R is 2 or 4");
+          fwd_stepR<L, R>(taps, [&](int q) { return cur[pad2(R * g + q)]; }, lo, hi);
+          if (!last) nxt[pad2(g)] = make_double2(lo[0], lo[1]);
+          else *reinterpret_cast<double2*>(dA + R * g) = make_double2(lo[0], lo[1]);
+          if (R * g < n_det) *reinterpret_cast<double2*>(dD + R * g) = make_double2(hi[0], hi[1]);
         }
-        if (kR * g < n_det) st_global_v4(dD + kR * g, hi[0], hi[1], hi[2], hi[3]);
       }
       __syncthreads();
       double2* t = cur; cur = nxt; nxt = t;
@@ -72,7 +80,7 @@ k_fwt_fwd(const __grid_constant__ Taps taps, const FwtFwdArgs a) {
     {
       const int per_line = h >> 1;            // double2 per line, >= 1
       const int total = nlines * per_line;
-      for (int it = tid; it < total; it += kThreads) {
+      for (int it = tid; it < total; it += nthr) {
         const int ln = it / per_line, k2 = it - ln * per_line;
         cp_async16(&bufA[ln * capA + pad2(k2)], a.src + (line0 + ln) * a.src_os + 2 * k2);
       }
@@ -87,7 +95,7 @@ k_fwt_fwd(const __grid_constant__ Taps taps, const FwtFwdArgs a) {
       const int mask2 = (h_in >> 1) - 1;      // wrap mask in double2 units
       const bool last = (k == m);
       const int items = nlines * gpl;
-      for (int it = tid; it < items; it += kThreads) {
+      for (int it = tid; it < items; it += nthr) {
         const int ln = it / gpl, g = it - ln * gpl;
         const double2* cl = cur + ln * cur_cap;
         double lo[kR], hi[kR];
@@ -147,12 +155,12 @@ static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, FwtFwdArgs a, bool r
     smem = size_t(a.G) * (a.cap0 + a.cap1) * sizeof(double2);
     grid = int((a.lines + a.G - 1) / a.G);
   }
-  auto kern = resident ? k_fwt_fwd<L, true> : k_fwt_fwd<L, false>;
+  auto kern = resident ? k_fwt_fwd<L, true> : (ctx->fwd_r == 2 ? k_fwt_fwd<L, false, 2> : k_fwt_fwd<L, false, 4>);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
   }
-  kern<<<grid, kThreads, smem, ctx->stream>>>(taps, a);
+  kern<<<grid, resident ? kThreads : ctx->fwd_threads, smem, ctx->stream>>>(taps, a);
   ctx->launches++;
   return cudaGetLastError();
 }

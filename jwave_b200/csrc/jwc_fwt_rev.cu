@@ -52,10 +52,10 @@ __device__ __forceinline__ void rev_step(const Taps& taps, A2 a2, D2 d2, double 
 }
 
 template <int L, bool RESIDENT, int kRS>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(384)
 k_fwt_rev(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevArgs a) {
   extern __shared__ double2 smem2[];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, nthr = blockDim.x;
   const int m = a.m, h0 = a.h0;
 
   if constexpr (!RESIDENT) {
@@ -71,12 +71,12 @@ k_fwt_rev(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevArgs 
       const int O = (k == m) ? ((t0 >> k) - a.F[k] - a.ru8) : 2 * ((t0 >> (k + 1)) - a.F[k + 1]);
       double2* D = smem2 + a.offD[k];
       const double* dk = lineD + wk;
-      for (int j2 = tid; j2 < a.len[k] / 2; j2 += kThreads)
+      for (int j2 = tid; j2 < a.len[k] / 2; j2 += nthr)
         cp_async16(&D[pad2(j2)], dk + ((O + 2 * j2) & (wk - 1)));
       if (k == m) {
         double2* A = smem2 + a.offA[m & 1];
         const double* am = a.srcA + line * a.srcA_os;
-        for (int j2 = tid; j2 < a.len[k] / 2; j2 += kThreads)
+        for (int j2 = tid; j2 < a.len[k] / 2; j2 += nthr)
           cp_async16(&A[pad2(j2)], am + ((O + 2 * j2) & (wk - 1)));
       }
     }
@@ -84,12 +84,14 @@ k_fwt_rev(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevArgs 
     __syncthreads();
 
     for (int k = m; k >= 1; --k) {
+      if (a.dbg == 2 && k > 1) continue;   // timing experiment: only the last level
+      if (a.dbg == 3) break;               // timing experiment: load only
       const double2* A = smem2 + a.offA[k & 1];
       const double2* D = smem2 + a.offD[k];
       double2* Y = smem2 + a.offA[(k - 1) & 1];
       const int groups = ((T >> k) + a.F[k]) / kRS;
       const int g0 = a.g0[k];
-      for (int g = tid; g < groups; g += kThreads) {
+      for (int g = tid; g < groups; g += nthr) {
         double t[2 * kRS];
         if constexpr (kRS == 8) {
           // pad2(4g' + 3 - w) = 5g' + (3 - w) + floor((3 - w) / 4): a compile-time offset per w
@@ -103,10 +105,11 @@ k_fwt_rev(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevArgs 
         if (k > 1) {
 #pragma unroll
           for (int e = 0; e < kRS; ++e) Y[pad2(kRS * g + e)] = make_double2(t[2 * e], t[2 * e + 1]);
-        } else {
+        } else if (a.dbg != 1 || t[0] == 123.456) {   // dbg 1: timing experiment without the stores
           double* y = a.dst + line * a.dst_os + t0 + 2 * kRS * g;
 #pragma unroll
           for (int e = 0; e < kRS / 2; ++e) st_global_v4(y + 4 * e, t[4 * e], t[4 * e + 1], t[4 * e + 2], t[4 * e + 3]);
+          static_assert(kRS >= 2, "a group stores at least 4 samples");
         }
       }
       __syncthreads();
@@ -122,7 +125,7 @@ k_fwt_rev(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevArgs 
     const int capP[2] = {capP0, capP1};
     {
       const int per_line = h0 >> 1;
-      for (int it = tid; it < nlines * per_line; it += kThreads) {
+      for (int it = tid; it < nlines * per_line; it += nthr) {
         const int ln = it / per_line, k2 = it - ln * per_line;
         cp_async16(&C[ln * capC + pad2(k2)], a.srcD + (line0 + ln) * a.srcD_os + 2 * k2);
       }
@@ -137,7 +140,7 @@ k_fwt_rev(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevArgs 
         const int gpl = half / kRS;
         const int mask2 = (half >> 1) - 1;
         const int doff = half >> 1;  // d_k starts at sample `half` of the prefix
-        for (int it = tid; it < nlines * gpl; it += kThreads) {
+        for (int it = tid; it < nlines * gpl; it += nthr) {
           const int ln = it / gpl, g = it - ln * gpl;
           const double2* cl = C + ln * capC;
           const double2* al = from_c ? cl : P[k & 1] + ln * capP[k & 1];
@@ -153,12 +156,13 @@ k_fwt_rev(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevArgs 
             double* y = a.dst + (line0 + ln) * a.dst_os + 2 * kRS * g;
 #pragma unroll
             for (int e = 0; e < kRS / 2; ++e) st_global_v4(y + 4 * e, t[4 * e], t[4 * e + 1], t[4 * e + 2], t[4 * e + 3]);
+          static_assert(kRS >= 2, "a group stores at least 4 samples");
           }
         }
       } else {
         // widths 2, 4, 8: one thread per (line, slot), true modular indexing (h < L wraps)
         const int mask = half - 1;
-        for (int it = tid; it < nlines * half; it += kThreads) {
+        for (int it = tid; it < nlines * half; it += nthr) {
           const int ln = it / half, p = it - ln * half;
           const double2* cl = C + ln * capC;
           const double2* al = from_c ? cl : P[k & 1] + ln * capP[k & 1];
@@ -226,13 +230,13 @@ static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, FwtRevArgs a, bool r
     smem = size_t(a.G) * (a.capC + a.capP[0] + a.capP[1]) * sizeof(double2);
     grid = int((a.lines + a.G - 1) / a.G);
   }
-  auto kern = resident ? (ctx->rev_rs == 4 ? k_fwt_rev<L, true, 4> : k_fwt_rev<L, true, 8>)
-                       : (ctx->rev_rs == 4 ? k_fwt_rev<L, false, 4> : k_fwt_rev<L, false, 8>);
+  auto kern = resident ? (ctx->rev_rs == 4 ? k_fwt_rev<L, true, 4> : ctx->rev_rs == 2 ? k_fwt_rev<L, true, 2> : k_fwt_rev<L, true, 8>)
+                       : (ctx->rev_rs == 4 ? k_fwt_rev<L, false, 4> : ctx->rev_rs == 2 ? k_fwt_rev<L, false, 2> : k_fwt_rev<L, false, 8>);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
   }
-  kern<<<grid, kThreads, smem, ctx->stream>>>(taps, a);
+  kern<<<grid, resident ? kThreads : ctx->rev_threads, smem, ctx->stream>>>(taps, a);
   ctx->launches++;
   return cudaGetLastError();
 }

@@ -272,7 +272,7 @@ static cudaError_t fwt_reverse(jwc_ctx* ctx, const WaveletRec& w, const double* 
   for (int i = 0; i < npass; ++i) {
     const Pass& p = passes[i];
     const bool last = (p.h0 == n);
-    a.h0 = p.h0; a.m = p.m;
+    a.h0 = p.h0; a.m = p.m; a.dbg = ctx->dbg;
     a.T = p.resident ? p.h0 : ctx->rev_tile;
     a.G = p.resident ? cap / p.h0 : 1;
     a.dst = last ? out : S[i & 1];
