@@ -96,6 +96,7 @@ extern "C" int jwc_create(jwc_ctx** out, int device) {
     get("res_cap", &ctx->res_cap);
     get("wpt_tile", &ctx->wpt_tile);
     get("wpt_m", &ctx->wpt_m);
+    get("wpt_rs", &ctx->wpt_rs);
     get("str_tile", &ctx->str_tile);
     get("str_rev_tile", &ctx->str_rev_tile);
     get("str_rev_m", &ctx->str_rev_m);

@@ -169,32 +169,46 @@ static cudaError_t fwt_forward(jwc_ctx* ctx, const WaveletRec& w, const double* 
                                int64_t outer, int n, int64_t inner, int level) {
   if (inner > 1 && strided_ok(ctx, in, out, n, inner)) return fwt_forward_strided(ctx, w, in, out, outer, n, inner, level);
   if (!fused_ok(ctx, in, out, n, inner)) return fwt_forward_generic(ctx, w, in, out, outer, n, inner, level);
-  const int cap = ctx->res_cap, tileT = ctx->fwd_tile;
-  int m_tile = fwt_tile_levels(w.L, tileT);
-  if (ctx->fwd_m > 0 && ctx->fwd_m < m_tile) m_tile = ctx->fwd_m;
-  double* S[2] = {nullptr, nullptr};
-  if (n > cap && level > m_tile) {
-    JWC_TRY(ensure_scratch(ctx, 1, size_t(outer) * (n >> m_tile) * sizeof(double), &S[1]));
-    if ((n >> m_tile) > cap && level > 2 * m_tile)
-      JWC_TRY(ensure_scratch(ctx, 0, size_t(outer) * (n >> (2 * m_tile)) * sizeof(double), &S[0]));
+  const int cap = ctx->res_cap;
+  struct Pass { int h, T, m; bool resident; };
+  Pass passes[32];
+  int npass = 0;
+  size_t need[2] = {0, 0};
+  for (int h = n, left = level; left > 0;) {
+    Pass p;
+    p.h = h;
+    p.resident = (h <= cap);
+    p.T = p.resident ? h : (h < ctx->fwd_tile ? h : ctx->fwd_tile);
+    if (p.resident) {
+      p.m = left;
+    } else {
+      int m_tile = fwt_tile_levels(w.L, p.T);
+      if (ctx->fwd_m > 0 && ctx->fwd_m < m_tile) m_tile = ctx->fwd_m;
+      p.m = left < m_tile ? left : m_tile;
+    }
+    if (p.m < left) {  // a_m of this pass goes to compact scratch lines
+      const size_t bytes = size_t(outer) * (h >> p.m) * sizeof(double);
+      if (bytes > need[(npass + 1) & 1]) need[(npass + 1) & 1] = bytes;
+    }
+    passes[npass++] = p;
+    h >>= p.m; left -= p.m;
   }
+  double* S[2] = {nullptr, nullptr};
+  for (int i = 0; i < 2; ++i)
+    if (need[i]) JWC_TRY(ensure_scratch(ctx, i, need[i], &S[i]));
   FwtFwdArgs a;
   a.src = in; a.src_os = n;
   a.dstD = out; a.dstD_os = n;
   a.lines = outer;
-  int h = n, left = level, pass = 0;
-  while (left > 0) {
-    const bool resident = (h <= cap);
-    a.h = h;
-    a.T = resident ? h : tileT;
-    a.m = resident ? left : (left < m_tile ? left : m_tile);
-    a.G = resident ? cap / h : 1;
-    const bool last = (a.m == left);
-    a.dstA = last ? out : S[(pass + 1) & 1];
-    a.dstA_os = last ? n : (h >> a.m);
-    JWC_TRY(launch_fwt_fwd(ctx, w.L, w.de, a, resident));
+  for (int i = 0; i < npass; ++i) {
+    const Pass& p = passes[i];
+    const bool last = (i == npass - 1);
+    a.h = p.h; a.T = p.T; a.m = p.m;
+    a.G = p.resident ? (cap / p.h > 0 ? cap / p.h : 1) : 1;
+    a.dstA = last ? out : S[(i + 1) & 1];
+    a.dstA_os = last ? n : (p.h >> p.m);
+    JWC_TRY(launch_fwt_fwd(ctx, w.L, w.de, a, p.resident));
     a.src = a.dstA; a.src_os = a.dstA_os;
-    h >>= a.m; left -= a.m; ++pass;
   }
   return cudaSuccess;
 }
@@ -242,12 +256,14 @@ static cudaError_t fwt_reverse(jwc_ctx* ctx, const WaveletRec& w, const double* 
   int nw = 0;
   const int cur0 = n >> level;
   const int cap = ctx->res_cap;
-  int rev_m = ctx->rev_m;
-  while ((ctx->rev_tile >> rev_m) < 8) --rev_m;  // a tile keeps >= 8 slots at its coarsest level
-  for (int wv = n; wv > cur0; wv >>= rev_m) {
+  for (int wv = n; wv > cur0;) {
     widths[nw++] = wv;
     if (wv <= cap) break;  // this one is produced by the resident pass
+    const int T = wv < ctx->rev_tile ? wv : ctx->rev_tile;
+    int rev_m = ctx->rev_m;
+    while ((T >> rev_m) < 8) --rev_m;  // a tile keeps >= 8 slots at its coarsest level
     if ((wv >> rev_m) <= cur0) break;
+    wv >>= rev_m;
   }
   for (int i = nw - 1, cur = cur0; i >= 0; --i) {
     Pass p;
@@ -273,8 +289,8 @@ static cudaError_t fwt_reverse(jwc_ctx* ctx, const WaveletRec& w, const double* 
     const Pass& p = passes[i];
     const bool last = (p.h0 == n);
     a.h0 = p.h0; a.m = p.m; a.dbg = ctx->dbg;
-    a.T = p.resident ? p.h0 : ctx->rev_tile;
-    a.G = p.resident ? cap / p.h0 : 1;
+    a.T = (p.resident || p.h0 < ctx->rev_tile) ? p.h0 : ctx->rev_tile;
+    a.G = p.resident ? (cap / p.h0 > 0 ? cap / p.h0 : 1) : 1;
     a.dst = last ? out : S[i & 1];
     a.dst_os = last ? n : p.h0;
     JWC_TRY(launch_fwt_rev(ctx, w.L, w.re, a, p.resident));
@@ -342,7 +358,7 @@ static cudaError_t wpt_forward(jwc_ctx* ctx, const WaveletRec& w, const double* 
     Pass p;
     p.h = h;
     p.resident = (h <= ctx->res_cap);
-    p.m = p.resident ? left : wpt_tile_levels(w.L, ctx->wpt_tile, left < ctx->wpt_m ? left : ctx->wpt_m, kWptSmemLimit);
+    p.m = p.resident ? left : wpt_tile_levels(w.L, h < ctx->wpt_tile ? h : ctx->wpt_tile, left < ctx->wpt_m ? left : ctx->wpt_m, kWptSmemLimit);
     passes[npass++] = p;
     h >>= p.m; left -= p.m;
   }
@@ -356,7 +372,7 @@ static cudaError_t wpt_forward(jwc_ctx* ctx, const WaveletRec& w, const double* 
     a.dst = ((npass - 1 - i) & 1) ? S : out; a.dst_os = p.h;
     a.lines = outer * (n / p.h);
     a.h = p.h; a.m = p.m;
-    a.T = p.resident ? p.h : ctx->wpt_tile;
+    a.T = (p.resident || p.h < ctx->wpt_tile) ? p.h : ctx->wpt_tile;
     a.G = p.resident ? ctx->res_cap / p.h : 1;
     JWC_TRY(launch_wpt_fwd(ctx, w.L, w.de, a, p.resident));
     src = a.dst;
@@ -381,7 +397,7 @@ static cudaError_t wpt_reverse(jwc_ctx* ctx, const WaveletRec& w, const double* 
     int want = 0;
     while ((cur0 << want) < wv) ++want;
     if (want > ctx->wpt_m) want = ctx->wpt_m;
-    wv >>= wpt_rev_tile_levels(w.L, ctx->wpt_tile, want, kWptSmemLimit);
+    wv >>= wpt_rev_tile_levels(w.L, wv < ctx->wpt_tile ? wv : ctx->wpt_tile, want, kWptSmemLimit);
   }
   for (int i = nw - 1, cur = cur0; i >= 0; --i) {
     Pass p;
@@ -402,7 +418,7 @@ static cudaError_t wpt_reverse(jwc_ctx* ctx, const WaveletRec& w, const double* 
     a.dst = ((npass - 1 - i) & 1) ? S : out; a.dst_os = p.h0;
     a.lines = outer * (n / p.h0);
     a.h0 = p.h0; a.m = p.m;
-    a.T = p.resident ? p.h0 : ctx->wpt_tile;
+    a.T = (p.resident || p.h0 < ctx->wpt_tile) ? p.h0 : ctx->wpt_tile;
     a.G = p.resident ? ctx->res_cap / p.h0 : 1;
     JWC_TRY(launch_wpt_rev(ctx, w.L, w.re, a, p.resident));
     src = a.dst;

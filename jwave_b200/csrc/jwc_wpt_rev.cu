@@ -18,20 +18,18 @@
 
 namespace jwc {
 
-constexpr int kRS = 8;  // coefficient slots (=> 16 time samples) per thread and step
-
-// identical to jwc_fwt_rev.cu: 8 slots p = 8g'..8g'+7 -> t[16]; a2(w)/d2(w) = double2 (4g'+3-w)
-template <int L, class A2, class D2>
-__device__ __forceinline__ void rev_step8(const Taps& taps, A2 a2, D2 d2, double (&t)[2 * kRS]) {
+// RS consecutive slots -> t[2 RS]; a2(w)/d2(w) = double2 (RS/2 g' + RS/2 - 1 - w); see jwc_fwt_rev.cu
+template <int L, int RS, class A2, class D2>
+__device__ __forceinline__ void wrev_step(const Taps& taps, A2 a2, D2 d2, double (&t)[2 * RS]) {
 #pragma unroll
-  for (int r = 0; r < 2 * kRS; ++r) t[r] = 0.0;
-  constexpr int W = (L / 2) / 2 + 4;
+  for (int r = 0; r < 2 * RS; ++r) t[r] = 0.0;
+  constexpr int W = (L / 2) / 2 + RS / 2;
 #pragma unroll
   for (int w = 0; w < W; ++w) {
     const double2 av = a2(w), dv = d2(w);
 #pragma unroll
-    for (int pp = 0; pp < kRS; ++pp) {
-      const int qy = pp - 7 + 2 * w;
+    for (int pp = 0; pp < RS; ++pp) {
+      const int qy = pp - (RS - 1) + 2 * w;
       const int qx = qy + 1;
       if (qy >= 0 && qy < L / 2) {
         t[2 * pp] = fma(av.y, taps.lo[2 * qy], t[2 * pp]);
@@ -49,7 +47,7 @@ __device__ __forceinline__ void rev_step8(const Taps& taps, A2 a2, D2 d2, double
   }
 }
 
-template <int L, bool RESIDENT>
+template <int L, bool RESIDENT, int kRS>
 __global__ void __launch_bounds__(512)
 k_wpt_rev(const __grid_constant__ Taps taps, const __grid_constant__ WptRevArgs a) {
   extern __shared__ double2 smem2[];
@@ -85,11 +83,18 @@ k_wpt_rev(const __grid_constant__ Taps taps, const __grid_constant__ WptRevArgs 
       const int items = groups << (k - 1);
       for (int it = tid; it < items; it += nthr) {
         const int par = it / groups, g = it - par * groups;
-        const double2* A = cur + (2 * par) * cap_in + base0 + 5 * g;   // pad2(4g'+3-w) = 5g' + (3-w) + floor((3-w)/4)
-        const double2* D = A + cap_in;
         double t[2 * kRS];
-        rev_step8<L>(taps, [&](int w) { return A[(3 - w) + ((3 - w) >> 2)]; },
-                     [&](int w) { return D[(3 - w) + ((3 - w) >> 2)]; }, t);
+        if constexpr (kRS == 8) {
+          const double2* A = cur + (2 * par) * cap_in + base0 + 5 * g;   // pad2(4g'+3-w) = 5g' + (3-w) + floor((3-w)/4)
+          const double2* D = A + cap_in;
+          wrev_step<L, 8>(taps, [&](int w) { return A[(3 - w) + ((3 - w) >> 2)]; },
+                          [&](int w) { return D[(3 - w) + ((3 - w) >> 2)]; }, t);
+        } else {
+          const double2* A = cur + (2 * par) * cap_in;
+          const double2* D = A + cap_in;
+          const int c = 4 * a.g0[k] + (kRS / 2) * g + kRS / 2 - 1;
+          wrev_step<L, kRS>(taps, [&](int w) { return A[pad2(c - w)]; }, [&](int w) { return D[pad2(c - w)]; }, t);
+        }
         if (k > 1) {
           double2* Y = nxt + par * cap_out;
 #pragma unroll
@@ -97,7 +102,7 @@ k_wpt_rev(const __grid_constant__ Taps taps, const __grid_constant__ WptRevArgs 
         } else {
           double* y = a.dst + line * a.dst_os + t0 + 2 * kRS * g;
 #pragma unroll
-          for (int e = 0; e < 4; ++e) st_global_v4(y + 4 * e, t[4 * e], t[4 * e + 1], t[4 * e + 2], t[4 * e + 3]);
+          for (int e = 0; e < kRS / 2; ++e) st_global_v4(y + 4 * e, t[4 * e], t[4 * e + 1], t[4 * e + 2], t[4 * e + 3]);
         }
       }
       __syncthreads();
@@ -132,9 +137,9 @@ k_wpt_rev(const __grid_constant__ Taps taps, const __grid_constant__ WptRevArgs 
           const int par = r / gpp, g = r - par * gpp;
           const double2* cl = cur + ln * cap;
           const int offA = (2 * par) * (half >> 1), offD = offA + (half >> 1);
-          const int c = 4 * g + 3;
+          const int c = (kRS / 2) * g + kRS / 2 - 1;
           double t[2 * kRS];
-          rev_step8<L>(taps, [&](int w) { return cl[pad2(offA + ((c - w) & mask2))]; },
+          wrev_step<L, kRS>(taps, [&](int w) { return cl[pad2(offA + ((c - w) & mask2))]; },
                        [&](int w) { return cl[pad2(offD + ((c - w) & mask2))]; }, t);
           if (!last) {
             double2* y = nxt + ln * cap;
@@ -144,7 +149,7 @@ k_wpt_rev(const __grid_constant__ Taps taps, const __grid_constant__ WptRevArgs 
           } else {
             double* y = a.dst + (line0 + ln) * a.dst_os + 2 * kRS * g;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) st_global_v4(y + 4 * e, t[4 * e], t[4 * e + 1], t[4 * e + 2], t[4 * e + 3]);
+            for (int e = 0; e < kRS / 2; ++e) st_global_v4(y + 4 * e, t[4 * e], t[4 * e + 1], t[4 * e + 2], t[4 * e + 3]);
           }
         }
       } else {
@@ -197,7 +202,7 @@ static size_t wpt_rev_tile_geometry(int L, WptRevArgs& a) {
   int cap = 0;
   for (int k = 1; k <= a.m; ++k) {
     a.len[k] = (k == a.m) ? (a.T >> k) + a.F[k] + a.ru8 : (a.T >> k) + 2 * a.F[k + 1];
-    a.g0[k] = (k == a.m) ? a.ru8 / kRS : (2 * a.F[k + 1] - a.F[k]) / kRS;
+    a.g0[k] = (k == a.m) ? a.ru8 / 8 : (2 * a.F[k + 1] - a.F[k]) / 8;
     a.cap[k] = pad2_size(a.len[k] / 2);
     const int c = (1 << k) * a.cap[k];
     if (c > cap) cap = c;
@@ -211,7 +216,7 @@ int wpt_rev_tile_levels(int L, int T, int want, size_t smem_limit) {
   WptRevArgs a;
   a.T = T;
   int m = 1;
-  while (m < want && m < kMaxFuse && (T >> (m + 1)) >= kRS) {
+  while (m < want && m < kMaxFuse && (T >> (m + 1)) >= 8) {
     a.m = m + 1;
     if (wpt_rev_tile_geometry(L, a) > smem_limit) break;
     ++m;
@@ -224,7 +229,7 @@ static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, WptRevArgs a, bool r
   size_t smem;
   int64_t grid;
   if (!resident) {
-    if (a.m < 1 || a.m > kMaxFuse || (a.T >> a.m) < kRS) return cudaErrorInvalidValue;
+    if (a.m < 1 || a.m > kMaxFuse || (a.T >> a.m) < 8) return cudaErrorInvalidValue;
     smem = wpt_rev_tile_geometry(L, a);
     a.tiles_per_line = a.h0 / a.T;
     grid = a.lines * a.tiles_per_line;
@@ -234,7 +239,8 @@ static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, WptRevArgs a, bool r
     grid = (a.lines + a.G - 1) / a.G;
   }
   if (grid > 0x7fffffff) return cudaErrorInvalidConfiguration;
-  auto kern = resident ? k_wpt_rev<L, true> : k_wpt_rev<L, false>;
+  auto kern = resident ? (ctx->wpt_rs == 4 ? k_wpt_rev<L, true, 4> : k_wpt_rev<L, true, 8>)
+                       : (ctx->wpt_rs == 4 ? k_wpt_rev<L, false, 4> : k_wpt_rev<L, false, 8>);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
