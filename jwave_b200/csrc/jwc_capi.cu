@@ -97,6 +97,7 @@ extern "C" int jwc_create(jwc_ctx** out, int device) {
     get("wpt_tile", &ctx->wpt_tile);
     get("wpt_m", &ctx->wpt_m);
     get("wpt_rs", &ctx->wpt_rs);
+    get("wpt_r", &ctx->wpt_r);
     get("str_tile", &ctx->str_tile);
     get("str_rev_tile", &ctx->str_rev_tile);
     get("str_rev_m", &ctx->str_rev_m);
@@ -175,6 +176,13 @@ extern "C" int jwc_set_wavelet(jwc_ctx* ctx, int L, const double* sDe, const dou
     rec.de.hi[j] = wDe[j];
     rec.re.lo[j] = sRe[j];
     rec.re.hi[j] = wRe[j];
+  }
+  rec.mirror_de = rec.mirror_re = true;
+  for (int j = 0; j < L; ++j) {
+    const double de = (j & 1) ? -sDe[L - 1 - j] : sDe[L - 1 - j];
+    const double re = (j & 1) ? -sRe[L - 1 - j] : sRe[L - 1 - j];
+    if (memcmp(&de, &wDe[j], sizeof(double)) != 0) rec.mirror_de = false;
+    if (memcmp(&re, &wRe[j], sizeof(double)) != 0) rec.mirror_re = false;
   }
   ctx->wavelets.push_back(rec);
   *wid = int(ctx->wavelets.size()) - 1;

@@ -53,9 +53,9 @@ __device__ __forceinline__ void fwd_stepR(const Taps& taps, Win win, double (&lo
       const int jj = q - r;
       if (jj >= 0 && jj < L / 2) {
         lo[r] = fma(v.x, taps.lo[2 * jj], lo[r]);
-        hi[r] = fma(v.x, taps.hi[2 * jj], hi[r]);
+        hi[r] = fma(v.x, hi_tap<L>(taps, 2 * jj), hi[r]);
         lo[r] = fma(v.y, taps.lo[2 * jj + 1], lo[r]);
-        hi[r] = fma(v.y, taps.hi[2 * jj + 1], hi[r]);
+        hi[r] = fma(v.y, hi_tap<L>(taps, 2 * jj + 1), hi[r]);
       }
     }
   }
@@ -78,9 +78,9 @@ __device__ __forceinline__ void fwd_step4(const Taps& taps, Win win, double (&lo
       const int jj = q - r;  // tap pair index for output r
       if (jj >= 0 && jj < L / 2) {
         lo[r] = fma(v.x, taps.lo[2 * jj], lo[r]);
-        hi[r] = fma(v.x, taps.hi[2 * jj], hi[r]);
+        hi[r] = fma(v.x, hi_tap<L>(taps, 2 * jj), hi[r]);
         lo[r] = fma(v.y, taps.lo[2 * jj + 1], lo[r]);
-        hi[r] = fma(v.y, taps.hi[2 * jj + 1], hi[r]);
+        hi[r] = fma(v.y, hi_tap<L>(taps, 2 * jj + 1), hi[r]);
       }
     }
   }
@@ -102,9 +102,9 @@ __device__ __forceinline__ void rev_step4(const Taps& taps, Ca ca, Cd cd, double
       const int q = s - (kR - 1 - pp);  // a[4g+3-s] = a[(4g+pp) - q]
       if (q >= 0 && q < L / 2) {
         t[2 * pp] = fma(av, taps.lo[2 * q], t[2 * pp]);
-        t[2 * pp] = fma(dv, taps.hi[2 * q], t[2 * pp]);
+        t[2 * pp] = fma(dv, hi_tap<L>(taps, 2 * q), t[2 * pp]);
         t[2 * pp + 1] = fma(av, taps.lo[2 * q + 1], t[2 * pp + 1]);
-        t[2 * pp + 1] = fma(dv, taps.hi[2 * q + 1], t[2 * pp + 1]);
+        t[2 * pp + 1] = fma(dv, hi_tap<L>(taps, 2 * q + 1), t[2 * pp + 1]);
       }
     }
   }

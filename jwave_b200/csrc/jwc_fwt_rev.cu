@@ -37,15 +37,15 @@ __device__ __forceinline__ void rev_step(const Taps& taps, A2 a2, D2 d2, double 
       const int qx = qy + 1;                 // .x is the slot before it
       if (qy >= 0 && qy < L / 2) {
         t[2 * pp] = fma(av.y, taps.lo[2 * qy], t[2 * pp]);
-        t[2 * pp] = fma(dv.y, taps.hi[2 * qy], t[2 * pp]);
+        t[2 * pp] = fma(dv.y, hi_tap<L>(taps, 2 * qy), t[2 * pp]);
         t[2 * pp + 1] = fma(av.y, taps.lo[2 * qy + 1], t[2 * pp + 1]);
-        t[2 * pp + 1] = fma(dv.y, taps.hi[2 * qy + 1], t[2 * pp + 1]);
+        t[2 * pp + 1] = fma(dv.y, hi_tap<L>(taps, 2 * qy + 1), t[2 * pp + 1]);
       }
       if (qx >= 0 && qx < L / 2) {
         t[2 * pp] = fma(av.x, taps.lo[2 * qx], t[2 * pp]);
-        t[2 * pp] = fma(dv.x, taps.hi[2 * qx], t[2 * pp]);
+        t[2 * pp] = fma(dv.x, hi_tap<L>(taps, 2 * qx), t[2 * pp]);
         t[2 * pp + 1] = fma(av.x, taps.lo[2 * qx + 1], t[2 * pp + 1]);
-        t[2 * pp + 1] = fma(dv.x, taps.hi[2 * qx + 1], t[2 * pp + 1]);
+        t[2 * pp + 1] = fma(dv.x, hi_tap<L>(taps, 2 * qx + 1), t[2 * pp + 1]);
       }
     }
   }
@@ -172,9 +172,9 @@ k_fwt_rev(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevArgs 
             const int i = (p - q) & mask;
             const double av = sm_scalar(al, i), dv = sm_scalar(cl, half + i);
             t0v = fma(av, taps.lo[2 * q], t0v);
-            t0v = fma(dv, taps.hi[2 * q], t0v);
+            t0v = fma(dv, hi_tap<L>(taps, 2 * q), t0v);
             t1v = fma(av, taps.lo[2 * q + 1], t1v);
-            t1v = fma(dv, taps.hi[2 * q + 1], t1v);
+            t1v = fma(dv, hi_tap<L>(taps, 2 * q + 1), t1v);
           }
           if (!last) {
             P[(k - 1) & 1][ln * capP[(k - 1) & 1] + pad2(p)] = make_double2(t0v, t1v);

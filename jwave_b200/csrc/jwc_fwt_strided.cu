@@ -83,7 +83,7 @@ k_fwt_fwd_str(const __grid_constant__ Taps taps, const FwtFwdStrArgs a) {
           for (int j = 0; j < L; ++j) {
             const double v = sat(cur, (2 * i + j) & mask, c);
             lo = fma(v, taps.lo[j], lo);
-            hi = fma(v, taps.hi[j], hi);
+            hi = fma(v, hi_tap<L>(taps, j), hi);
           }
           if (!last) sat(nxt, i, c) = lo;
           else gA[int64_t(i) * inner] = lo;
@@ -177,9 +177,9 @@ k_fwt_rev_str(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevS
             const int i = (p - q) & mask;
             const double av = sat(A, i, c), dv = sat(C, half + i, c);
             t0v = fma(av, taps.lo[2 * q], t0v);
-            t0v = fma(dv, taps.hi[2 * q], t0v);
+            t0v = fma(dv, hi_tap<L>(taps, 2 * q), t0v);
             t1v = fma(av, taps.lo[2 * q + 1], t1v);
-            t1v = fma(dv, taps.hi[2 * q + 1], t1v);
+            t1v = fma(dv, hi_tap<L>(taps, 2 * q + 1), t1v);
           }
           if (!last) { sat(Y, 2 * p, c) = t0v; sat(Y, 2 * p + 1, c) = t1v; }
           else { gY[int64_t(2 * p) * inner] = t0v; gY[int64_t(2 * p + 1) * inner] = t1v; }

@@ -18,7 +18,18 @@ struct Taps {
   double hi[JWC_MAX_TAPS];  // wavelet (high pass)
 };
 
+// Every in-scope family builds its high pass from the low pass (Wavelet.java:104-122; Haar1.java:62
+// writes the same thing out by hand): hi[j] = (j even ? + : -) lo[L - 1 - j].  The fused kernels use
+// that: only the L low-pass taps have to stay in uniform registers (2L do not fit for L >= 16, and
+// ptxas then shuffles taps between register files inside the inner loop).  jwc_set_wavelet checks the
+// relation bit for bit; filter sets without it run on the one-level kernels, which use both arrays.
+template <int L>
+__device__ __forceinline__ double hi_tap(const Taps& t, int j) {
+  return (j & 1) ? -t.lo[L - 1 - j] : t.lo[L - 1 - j];
+}
+
 struct WaveletRec {
+  bool mirror_de, mirror_re;  // the relation above holds for the decomposition / reconstruction pair
   int L;
   Taps de;  // decomposition: _scalingDeCom / _waveletDeCom
   Taps re;  // reconstruction: _scalingReCon / _waveletReCon
@@ -47,7 +58,7 @@ struct jwc_ctx {
   size_t staging_bytes = size_t(256) << 20;
   bool force_generic = false;   // JWC_FORCE_GENERIC=1: only the one-level reference kernels
   // launch-shape tunables (JWC_TUNE="fwd_tile=2048,fwd_m=5,rev_tile=4096,rev_m=5,res_cap=4096")
-  int fwd_tile = 2048, fwd_m = 4 /* cap on the halo rule */, fwd_r = 4, rev_tile = 2048, rev_m = 4, rev_rs = 4, dbg = 0, fwd_threads = 128, rev_threads = 128, res_cap = 256, wpt_tile = 2048, wpt_m = 3, wpt_threads = 128, wpt_rs = 8;
+  int fwd_tile = 2048, fwd_m = 4 /* cap on the halo rule */, fwd_r = 4, rev_tile = 2048, rev_m = 4, rev_rs = 4, dbg = 0, fwd_threads = 128, rev_threads = 128, res_cap = 256, wpt_tile = 2048, wpt_m = 3, wpt_threads = 128, wpt_rs = 8, wpt_r = 4;
   int str_tile = 1024, str_rev_tile = 512, str_rev_m = 5, str_cap = 512;  // strided-axis kernels
 };
 

@@ -72,7 +72,7 @@ struct WptFwdArgs {
   int h, m, T, G;
   int tiles_per_line, buf_cap;          // filled in by the launcher
 };
-int wpt_tile_levels(int L, int T, int want, size_t smem_limit);
+int wpt_tile_levels(int L, int T, int want, size_t smem_limit, int R);
 cudaError_t launch_wpt_fwd(jwc_ctx* ctx, int L, const Taps& taps, const WptFwdArgs& a, bool resident);
 
 // ---- reverse WPT, contiguous lines (jwc_wpt_rev.cu) -----------------------------------------

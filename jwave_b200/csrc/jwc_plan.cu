@@ -167,8 +167,8 @@ static cudaError_t fwt_reverse_strided(jwc_ctx* ctx, const WaveletRec& w, const 
 // launch for everything that is left.  a_m of a tile pass goes to a compact scratch buffer.
 static cudaError_t fwt_forward(jwc_ctx* ctx, const WaveletRec& w, const double* in, double* out,
                                int64_t outer, int n, int64_t inner, int level) {
-  if (inner > 1 && strided_ok(ctx, in, out, n, inner)) return fwt_forward_strided(ctx, w, in, out, outer, n, inner, level);
-  if (!fused_ok(ctx, in, out, n, inner)) return fwt_forward_generic(ctx, w, in, out, outer, n, inner, level);
+  if (inner > 1 && w.mirror_de && strided_ok(ctx, in, out, n, inner)) return fwt_forward_strided(ctx, w, in, out, outer, n, inner, level);
+  if (!w.mirror_de || !fused_ok(ctx, in, out, n, inner)) return fwt_forward_generic(ctx, w, in, out, outer, n, inner, level);
   const int cap = ctx->res_cap;
   struct Pass { int h, T, m; bool resident; };
   Pass passes[32];
@@ -243,8 +243,8 @@ static cudaError_t fwt_reverse_generic(jwc_ctx* ctx, const WaveletRec& w, const 
 // to rev_m levels each.  Intermediate approximations go to compact scratch lines.
 static cudaError_t fwt_reverse(jwc_ctx* ctx, const WaveletRec& w, const double* in, double* out,
                                int64_t outer, int n, int64_t inner, int level) {
-  if (inner > 1 && strided_ok(ctx, in, out, n, inner)) return fwt_reverse_strided(ctx, w, in, out, outer, n, inner, level);
-  if (!fused_ok(ctx, in, out, n, inner)) return fwt_reverse_generic(ctx, w, in, out, outer, n, inner, level);
+  if (inner > 1 && w.mirror_re && strided_ok(ctx, in, out, n, inner)) return fwt_reverse_strided(ctx, w, in, out, outer, n, inner, level);
+  if (!w.mirror_re || !fused_ok(ctx, in, out, n, inner)) return fwt_reverse_generic(ctx, w, in, out, outer, n, inner, level);
   struct Pass { int h0, m; bool resident; };
   Pass passes[32];
   int npass = 0;
@@ -350,7 +350,7 @@ static const size_t kWptSmemLimit = 112 * 1024;  // two CTAs per SM
 
 static cudaError_t wpt_forward(jwc_ctx* ctx, const WaveletRec& w, const double* in, double* out,
                                int64_t outer, int n, int64_t inner, int level) {
-  if (!fused_ok(ctx, in, out, n, inner) || n < 8) return wpt_forward_generic(ctx, w, in, out, outer, n, inner, level);
+  if (!w.mirror_de || !fused_ok(ctx, in, out, n, inner) || n < 8) return wpt_forward_generic(ctx, w, in, out, outer, n, inner, level);
   struct Pass { int h, m; bool resident; };
   Pass passes[32];
   int npass = 0;
@@ -358,7 +358,7 @@ static cudaError_t wpt_forward(jwc_ctx* ctx, const WaveletRec& w, const double* 
     Pass p;
     p.h = h;
     p.resident = (h <= ctx->res_cap);
-    p.m = p.resident ? left : wpt_tile_levels(w.L, h < ctx->wpt_tile ? h : ctx->wpt_tile, left < ctx->wpt_m ? left : ctx->wpt_m, kWptSmemLimit);
+    p.m = p.resident ? left : wpt_tile_levels(w.L, h < ctx->wpt_tile ? h : ctx->wpt_tile, left < ctx->wpt_m ? left : ctx->wpt_m, kWptSmemLimit, ctx->wpt_r);
     passes[npass++] = p;
     h >>= p.m; left -= p.m;
   }
@@ -382,7 +382,7 @@ static cudaError_t wpt_forward(jwc_ctx* ctx, const WaveletRec& w, const double* 
 
 static cudaError_t wpt_reverse(jwc_ctx* ctx, const WaveletRec& w, const double* in, double* out,
                                int64_t outer, int n, int64_t inner, int level) {
-  if (!fused_ok(ctx, in, out, n, inner) || n < 8) return wpt_reverse_generic(ctx, w, in, out, outer, n, inner, level);
+  if (!w.mirror_re || !fused_ok(ctx, in, out, n, inner) || n < 8) return wpt_reverse_generic(ctx, w, in, out, outer, n, inner, level);
   // Output widths of the passes, chosen backwards from n: each tile pass rebuilds as many levels
   // as its shared memory allows; whatever is left below res_cap is one resident pass.
   struct Pass { int h0, m; bool resident; };

@@ -42,7 +42,7 @@ __device__ __forceinline__ void fwd_run(const Taps& taps, X x, double (&lo)[R], 
       const int j = s - 2 * r;
       if (j >= 0 && j < L) {
         lo[r] = fma(v, taps.lo[j], lo[r]);
-        hi[r] = fma(v, taps.hi[j], hi[r]);
+        hi[r] = fma(v, hi_tap<L>(taps, j), hi[r]);
       }
     }
   }
@@ -63,9 +63,9 @@ __device__ __forceinline__ void rev_run(const Taps& taps, A a, D d, double (&t)[
       const int q = s - (RS - 1 - pp);
       if (q >= 0 && q < L / 2) {
         t[2 * pp] = fma(av, taps.lo[2 * q], t[2 * pp]);
-        t[2 * pp] = fma(dv, taps.hi[2 * q], t[2 * pp]);
+        t[2 * pp] = fma(dv, hi_tap<L>(taps, 2 * q), t[2 * pp]);
         t[2 * pp + 1] = fma(av, taps.lo[2 * q + 1], t[2 * pp + 1]);
-        t[2 * pp + 1] = fma(dv, taps.hi[2 * q + 1], t[2 * pp + 1]);
+        t[2 * pp + 1] = fma(dv, hi_tap<L>(taps, 2 * q + 1), t[2 * pp + 1]);
       }
     }
   }

@@ -22,7 +22,21 @@
 
 namespace jwc {
 
-template <int L, bool RESIDENT>
+// Layout of this kernel's shared-memory lines: one pad slot per R double2, so a thread that
+// produces R outputs (window = R + L/2 - 1 consecutive double2 from a multiple of R) is R + 1 slots
+// away from its neighbour - an odd stride, conflict-free LDS.128 for R = 4 and R = 8.  A longer run
+// per thread cuts shared-memory wavefronts per DFMA (L = 16: 11 LDS per 128 DFMA at R = 4, 15 per
+// 256 at R = 8), which is what bounds the long-filter WPT.
+template <int R> __device__ __forceinline__ int padr(int k2) { return k2 + (k2 / R); }
+template <int R> __host__ __device__ constexpr int padr_size(int n2) { return n2 + n2 / R + 2; }
+template <int R> __device__ __forceinline__ double lscalar(const double2* buf, int i) {
+  return reinterpret_cast<const double*>(buf)[2 * padr<R>(i >> 1) + (i & 1)];
+}
+template <int R> __device__ __forceinline__ void lscalar_store(double2* buf, int i, double v) {
+  reinterpret_cast<double*>(buf)[2 * padr<R>(i >> 1) + (i & 1)] = v;
+}
+
+template <int L, bool RESIDENT, int R>
 __global__ void __launch_bounds__(512)
 k_wpt_fwd(const __grid_constant__ Taps taps, const WptFwdArgs a) {
   extern __shared__ double2 smem2[];
@@ -40,7 +54,7 @@ k_wpt_fwd(const __grid_constant__ Taps taps, const WptFwdArgs a) {
     const double* src = a.src + line * a.src_os;
     const int base = tile * T;
     for (int k2 = tid; k2 < n0 / 2; k2 += nthr)
-      cp_async16(&cur[pad2(k2)], src + ((base + 2 * k2) & (h - 1)));
+      cp_async16(&cur[padr<R>(k2)], src + ((base + 2 * k2) & (h - 1)));
     cp_async_wait_all();
     __syncthreads();
 
@@ -49,26 +63,31 @@ k_wpt_fwd(const __grid_constant__ Taps taps, const WptFwdArgs a) {
     for (int k = 1; k <= m; ++k) {
       const int n_keep = T >> k;                                    // outputs of each node this tile owns
       const int n_out = n_keep + ((1 << (m - k)) - 1) * (L - 2);    // incl. halo for the levels below
-      const int groups = (n_out + kR - 1) / kR;
-      const int cap_out = pad2_size(n_out / 2 + 4);
+      const int groups = (n_out + R - 1) / R;
+      const int cap_out = padr_size<R>(n_out / 2 + R);
       const int items = groups << (k - 1);                          // nodes_in * groups
       const bool last = (k == m);
-      for (int it = tid; it < items; it += nthr) {
-        const int node = it / groups, g = it - node * groups;
-        const double2* w = cur + node * cap_in + 5 * g;             // pad2(4g + q) == 5g + q + (q >> 2)
-        double lo[kR], hi[kR];
-        fwd_step4<L>(taps, [&](int q) { return w[q + (q >> 2)]; }, lo, hi);
+      // (node, g) walk without a division: it = node * groups + g advances by nthr per step
+      for (int it = tid, node = tid / groups, g = tid - node * groups; it < items; it += nthr, g += nthr) {
+        while (g >= groups) { g -= groups; ++node; }
+        const double2* w = cur + node * cap_in + (R + 1) * g;        // padr(R g + q) == (R + 1) g + q + q / R
+        double lo[R], hi[R];
+        fwd_stepR<L, R>(taps, [&](int q) { return w[q + q / R]; }, lo, hi);
         if (!last) {
           double2* na = nxt + (2 * node) * cap_out;
           double2* nd = na + cap_out;
-          na[pad2(2 * g)] = make_double2(lo[0], lo[1]);
-          na[pad2(2 * g + 1)] = make_double2(lo[2], lo[3]);
-          nd[pad2(2 * g)] = make_double2(hi[0], hi[1]);
-          nd[pad2(2 * g + 1)] = make_double2(hi[2], hi[3]);
-        } else if (kR * g < n_keep) {
-          double* pa = outl + int64_t(2 * node) * (h >> m) + tile * n_keep + kR * g;
-          st_global_v4(pa, lo[0], lo[1], lo[2], lo[3]);
-          st_global_v4(pa + (h >> m), hi[0], hi[1], hi[2], hi[3]);
+#pragma unroll
+          for (int e = 0; e < R / 2; ++e) {
+            na[padr<R>(R / 2 * g + e)] = make_double2(lo[2 * e], lo[2 * e + 1]);
+            nd[padr<R>(R / 2 * g + e)] = make_double2(hi[2 * e], hi[2 * e + 1]);
+          }
+        } else if (R * g < n_keep) {
+          double* pa = outl + int64_t(2 * node) * (h >> m) + tile * n_keep + R * g;
+#pragma unroll
+          for (int e = 0; e < R / 4; ++e) {
+            st_global_v4(pa + 4 * e, lo[4 * e], lo[4 * e + 1], lo[4 * e + 2], lo[4 * e + 3]);
+            st_global_v4(pa + (h >> m) + 4 * e, hi[4 * e], hi[4 * e + 1], hi[4 * e + 2], hi[4 * e + 3]);
+          }
         }
       }
       __syncthreads();
@@ -87,7 +106,7 @@ k_wpt_fwd(const __grid_constant__ Taps taps, const WptFwdArgs a) {
       const int per_line = h >> 1;
       for (int it = tid; it < nlines * per_line; it += nthr) {
         const int ln = it / per_line, k2 = it - ln * per_line;
-        cp_async16(&cur[ln * cap + pad2(k2)], a.src + (line0 + ln) * a.src_os + 2 * k2);
+        cp_async16(&cur[ln * cap + padr<R>(k2)], a.src + (line0 + ln) * a.src_os + 2 * k2);
       }
       cp_async_wait_all();
       __syncthreads();
@@ -96,8 +115,8 @@ k_wpt_fwd(const __grid_constant__ Taps taps, const WptFwdArgs a) {
       const int h_in = h >> (k - 1), h_out = h_in >> 1;   // node length before / after this level
       const int lg_nodes = k - 1;                          // nodes per line at the input level = 2^(k-1)
       const bool last = (k == m);
-      if (h_out >= kR) {
-        const int gpn = h_out / kR;                        // groups per node (power of two)
+      if (h_out >= R) {
+        const int gpn = h_out / R;                        // groups per node (power of two)
         const int per_line = gpn << lg_nodes;              // == h / 8
         const int mask2 = (h_in >> 1) - 1;
         for (int it = tid; it < nlines * per_line; it += nthr) {
@@ -105,23 +124,27 @@ k_wpt_fwd(const __grid_constant__ Taps taps, const WptFwdArgs a) {
           const int node = r / gpn, g = r - node * gpn;
           const double2* cl = cur + ln * cap;
           const int off2 = node * (h_in >> 1);             // node start inside the line (double2)
-          double lo[kR], hi[kR];
-          fwd_step4<L>(taps, [&](int q) { return cl[pad2(off2 + ((kR * g + q) & mask2))]; }, lo, hi);
+          double lo[R], hi[R];
+          fwd_stepR<L, R>(taps, [&](int q) { return cl[padr<R>(off2 + ((R * g + q) & mask2))]; }, lo, hi);
           if (!last) {
             double2* nl = nxt + ln * cap;
-            const int oa = (2 * node) * (h_out >> 1) + 2 * g, od = oa + (h_out >> 1);
-            nl[pad2(oa)] = make_double2(lo[0], lo[1]);
-            nl[pad2(oa + 1)] = make_double2(lo[2], lo[3]);
-            nl[pad2(od)] = make_double2(hi[0], hi[1]);
-            nl[pad2(od + 1)] = make_double2(hi[2], hi[3]);
+            const int oa = (2 * node) * (h_out >> 1) + R / 2 * g, od = oa + (h_out >> 1);
+#pragma unroll
+            for (int e = 0; e < R / 2; ++e) {
+              nl[padr<R>(oa + e)] = make_double2(lo[2 * e], lo[2 * e + 1]);
+              nl[padr<R>(od + e)] = make_double2(hi[2 * e], hi[2 * e + 1]);
+            }
           } else {
-            double* pa = a.dst + (line0 + ln) * a.dst_os + int64_t(2 * node) * h_out + kR * g;
-            st_global_v4(pa, lo[0], lo[1], lo[2], lo[3]);
-            st_global_v4(pa + h_out, hi[0], hi[1], hi[2], hi[3]);
+            double* pa = a.dst + (line0 + ln) * a.dst_os + int64_t(2 * node) * h_out + R * g;
+#pragma unroll
+            for (int e = 0; e < R / 4; ++e) {
+              st_global_v4(pa + 4 * e, lo[4 * e], lo[4 * e + 1], lo[4 * e + 2], lo[4 * e + 3]);
+              st_global_v4(pa + h_out + 4 * e, hi[4 * e], hi[4 * e + 1], hi[4 * e + 2], hi[4 * e + 3]);
+            }
           }
         }
       } else {
-        // nodes of 2 or 4 samples in, 1 or 2 out: one thread per (line, node, i); true modular wrap
+        // nodes shorter than R outputs: one thread per (line, node, i); true modular wrap
         const int per_line = h_out << lg_nodes;            // == h / 2
         for (int it = tid; it < nlines * per_line; it += nthr) {
           const int ln = it / per_line, r = it - ln * per_line;
@@ -131,15 +154,15 @@ k_wpt_fwd(const __grid_constant__ Taps taps, const WptFwdArgs a) {
           double lo = 0.0, hi = 0.0;
 #pragma unroll
           for (int j = 0; j < L; ++j) {
-            const double x = sm_scalar(cl, off + ((2 * i + j) & (h_in - 1)));
+            const double x = lscalar<R>(cl, off + ((2 * i + j) & (h_in - 1)));
             lo = fma(x, taps.lo[j], lo);
-            hi = fma(x, taps.hi[j], hi);
+            hi = fma(x, hi_tap<L>(taps, j), hi);
           }
           const int oa = (2 * node) * h_out + i, od = oa + h_out;
           if (!last) {
             double2* nl = nxt + ln * cap;
-            sm_scalar_store(nl, oa, lo);
-            sm_scalar_store(nl, od, hi);
+            lscalar_store<R>(nl, oa, lo);
+            lscalar_store<R>(nl, od, hi);
           } else {
             double* pl = a.dst + (line0 + ln) * a.dst_os;
             pl[oa] = lo;
@@ -156,43 +179,44 @@ k_wpt_fwd(const __grid_constant__ Taps taps, const WptFwdArgs a) {
 // ---- host side ---------------------------------------------------------------------------------
 
 // Shared memory (bytes) of a tile-mode launch; also fills the per-buffer capacity.
-static size_t wpt_fwd_tile_smem(int L, int T, int m, int* buf_cap) {
-  int cap = pad2_size((T + ((1 << m) - 1) * (L - 2)) / 2 + 4);  // level 0: one node
+static size_t wpt_fwd_tile_smem(int L, int T, int m, int R, int* buf_cap) {
+  auto psize = [R](int n2) { return n2 + n2 / R + 2; };
+  int cap = psize((T + ((1 << m) - 1) * (L - 2)) / 2 + R);  // level 0: one node
   for (int k = 1; k < m; ++k) {                                   // levels kept in shared memory
     const int n_out = (T >> k) + ((1 << (m - k)) - 1) * (L - 2);
-    const int c = (1 << k) * pad2_size(n_out / 2 + 4);
+    const int c = (1 << k) * psize(n_out / 2 + R);
     if (c > cap) cap = c;
   }
   *buf_cap = cap;
   return size_t(2) * cap * sizeof(double2);
 }
 
-int wpt_tile_levels(int L, int T, int want, size_t smem_limit) {
+int wpt_tile_levels(int L, int T, int want, size_t smem_limit, int R) {
   // as many levels as asked for, while the halo stays below T / 4, the leaf runs keep >= 4 samples
   // (32-byte stores) and two level buffers fit in shared memory
   int m = 1, cap;
-  while (m < want && ((1 << (m + 1)) - 1) * (L - 2) <= T / 4 && (T >> (m + 1)) >= kR &&
-         wpt_fwd_tile_smem(L, T, m + 1, &cap) <= smem_limit)
+  while (m < want && ((1 << (m + 1)) - 1) * (L - 2) <= T / 4 && (T >> (m + 1)) >= R &&
+         wpt_fwd_tile_smem(L, T, m + 1, R, &cap) <= smem_limit)
     ++m;
   return m;
 }
 
-template <int L>
-static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, WptFwdArgs a, bool resident) {
+template <int L, int R>
+static cudaError_t launch_LR(jwc_ctx* ctx, const Taps& taps, WptFwdArgs a, bool resident) {
   size_t smem;
   int64_t grid;
   if (!resident) {
-    if ((a.T >> a.m) < kR) return cudaErrorInvalidValue;
-    smem = wpt_fwd_tile_smem(L, a.T, a.m, &a.buf_cap);
+    if ((a.T >> a.m) < R) return cudaErrorInvalidValue;
+    smem = wpt_fwd_tile_smem(L, a.T, a.m, R, &a.buf_cap);
     a.tiles_per_line = a.h / a.T;
     grid = a.lines * a.tiles_per_line;
   } else {
-    a.buf_cap = pad2_size(max(1, a.h / 2));
+    a.buf_cap = padr_size<R>(max(1, a.h / 2));
     smem = size_t(2) * a.G * a.buf_cap * sizeof(double2);
     grid = (a.lines + a.G - 1) / a.G;
   }
   if (grid > 0x7fffffff) return cudaErrorInvalidConfiguration;
-  auto kern = resident ? k_wpt_fwd<L, true> : k_wpt_fwd<L, false>;
+  auto kern = resident ? k_wpt_fwd<L, true, R> : k_wpt_fwd<L, false, R>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
@@ -200,6 +224,11 @@ static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, WptFwdArgs a, bool r
   kern<<<int(grid), ctx->wpt_threads, smem, ctx->stream>>>(taps, a);
   ctx->launches++;
   return cudaGetLastError();
+}
+
+template <int L>
+static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, const WptFwdArgs& a, bool resident) {
+  return ctx->wpt_r == 8 ? launch_LR<L, 8>(ctx, taps, a, resident) : launch_LR<L, 4>(ctx, taps, a, resident);
 }
 
 cudaError_t launch_wpt_fwd(jwc_ctx* ctx, int L, const Taps& taps, const WptFwdArgs& a, bool resident) {

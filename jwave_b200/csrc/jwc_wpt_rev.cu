@@ -33,15 +33,15 @@ __device__ __forceinline__ void wrev_step(const Taps& taps, A2 a2, D2 d2, double
       const int qx = qy + 1;
       if (qy >= 0 && qy < L / 2) {
         t[2 * pp] = fma(av.y, taps.lo[2 * qy], t[2 * pp]);
-        t[2 * pp] = fma(dv.y, taps.hi[2 * qy], t[2 * pp]);
+        t[2 * pp] = fma(dv.y, hi_tap<L>(taps, 2 * qy), t[2 * pp]);
         t[2 * pp + 1] = fma(av.y, taps.lo[2 * qy + 1], t[2 * pp + 1]);
-        t[2 * pp + 1] = fma(dv.y, taps.hi[2 * qy + 1], t[2 * pp + 1]);
+        t[2 * pp + 1] = fma(dv.y, hi_tap<L>(taps, 2 * qy + 1), t[2 * pp + 1]);
       }
       if (qx >= 0 && qx < L / 2) {
         t[2 * pp] = fma(av.x, taps.lo[2 * qx], t[2 * pp]);
-        t[2 * pp] = fma(dv.x, taps.hi[2 * qx], t[2 * pp]);
+        t[2 * pp] = fma(dv.x, hi_tap<L>(taps, 2 * qx), t[2 * pp]);
         t[2 * pp + 1] = fma(av.x, taps.lo[2 * qx + 1], t[2 * pp + 1]);
-        t[2 * pp + 1] = fma(dv.x, taps.hi[2 * qx + 1], t[2 * pp + 1]);
+        t[2 * pp + 1] = fma(dv.x, hi_tap<L>(taps, 2 * qx + 1), t[2 * pp + 1]);
       }
     }
   }
@@ -81,8 +81,9 @@ k_wpt_rev(const __grid_constant__ Taps taps, const __grid_constant__ WptRevArgs 
       const int base0 = 5 * a.g0[k];
       const int cap_in = a.cap[k], cap_out = a.cap[k - 1];
       const int items = groups << (k - 1);
-      for (int it = tid; it < items; it += nthr) {
-        const int par = it / groups, g = it - par * groups;
+      // (parent, g) walk without a division: it = par * groups + g advances by nthr per step
+      for (int it = tid, par = tid / groups, g = tid - par * groups; it < items; it += nthr, g += nthr) {
+        while (g >= groups) { g -= groups; ++par; }
         double t[2 * kRS];
         if constexpr (kRS == 8) {
           const double2* A = cur + (2 * par) * cap_in + base0 + 5 * g;   // pad2(4g'+3-w) = 5g' + (3-w) + floor((3-w)/4)
@@ -167,9 +168,9 @@ k_wpt_rev(const __grid_constant__ Taps taps, const __grid_constant__ WptRevArgs 
             const int i = (p - q) & mask;
             const double av = sm_scalar(cl, offA + i), dv = sm_scalar(cl, offD + i);
             t0v = fma(av, taps.lo[2 * q], t0v);
-            t0v = fma(dv, taps.hi[2 * q], t0v);
+            t0v = fma(dv, hi_tap<L>(taps, 2 * q), t0v);
             t1v = fma(av, taps.lo[2 * q + 1], t1v);
-            t1v = fma(dv, taps.hi[2 * q + 1], t1v);
+            t1v = fma(dv, hi_tap<L>(taps, 2 * q + 1), t1v);
           }
           if (!last) {
             nxt[ln * cap + pad2(par * half + p)] = make_double2(t0v, t1v);

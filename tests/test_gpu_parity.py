@@ -187,6 +187,31 @@ def test_3d_level_shift_is_reproduced():
         t.forward(rng_signal(2, 4, 8, 16), 4, 3, 2)
 
 
+def test_independent_filters_take_the_one_level_kernels():
+    """The ABI accepts four independent filters (BiOrthogonal-style).  A set whose high pass is not
+    the mirrored low pass cannot use the fused kernels (they derive hi from lo) and must still be
+    right - checked against the numpy restatement with the same custom taps."""
+    from oracle import np_oracle as no
+    rng = np.random.default_rng(3)
+    L = 6
+    taps = tuple(rng.standard_normal(L) for _ in range(4))
+    no.WAVELETS["custom6"] = taps
+
+    class Custom(jw.Wavelet):
+        def __init__(self):
+            super().__init__("custom", taps[0], taps[1])
+            self._scalingReCon, self._waveletReCon = taps[2].copy(), taps[3].copy()
+
+    for T, f, r in ((jw.CudaFastWaveletTransform, no.fwt_forward, no.fwt_reverse),
+                    (jw.CudaWaveletPacketTransform, no.wpt_forward, no.wpt_reverse)):
+        t = T(Custom())
+        x = rng_signal(12, 512)
+        for level in (9, 3):
+            ref_f, ref_r = f("custom6", x, level), r("custom6", x, level)  # unnormalised taps: scale by the result
+            close(t.forward(x, level), ref_f, 10 * np.abs(ref_f).max())
+            close(t.reverse(x, level), ref_r, 10 * np.abs(ref_r).max())
+
+
 def test_abi_status_codes():
     """Raw C-ABI status codes (include/jwave_cuda.h) without the Python pre-checks."""
     import ctypes as C
