@@ -94,6 +94,7 @@ extern "C" int jwc_create(jwc_ctx** out, int device) {
     get("fwd_threads", &ctx->fwd_threads);
     get("rev_threads", &ctx->rev_threads);
     get("res_cap", &ctx->res_cap);
+    get("res_threads", &ctx->res_threads);
     get("wpt_tile", &ctx->wpt_tile);
     get("wpt_m", &ctx->wpt_m);
     get("wpt_rs", &ctx->wpt_rs);
@@ -102,6 +103,7 @@ extern "C" int jwc_create(jwc_ctx** out, int device) {
     get("str_rev_tile", &ctx->str_rev_tile);
     get("str_rev_m", &ctx->str_rev_m);
     get("str_cap", &ctx->str_cap);
+    get("str_threads", &ctx->str_threads);
     get("wpt_threads", &ctx->wpt_threads);
   }
   *out = ctx;

@@ -160,7 +160,7 @@ static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, FwtFwdArgs a, bool r
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
   }
-  kern<<<grid, resident ? kThreads : ctx->fwd_threads, smem, ctx->stream>>>(taps, a);
+  kern<<<grid, resident ? ctx->res_threads : ctx->fwd_threads, smem, ctx->stream>>>(taps, a);
   ctx->launches++;
   return cudaGetLastError();
 }

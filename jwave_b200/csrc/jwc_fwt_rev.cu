@@ -236,7 +236,7 @@ static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, FwtRevArgs a, bool r
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
   }
-  kern<<<grid, resident ? kThreads : ctx->rev_threads, smem, ctx->stream>>>(taps, a);
+  kern<<<grid, resident ? ctx->res_threads : ctx->rev_threads, smem, ctx->stream>>>(taps, a);
   ctx->launches++;
   return cudaGetLastError();
 }

@@ -19,6 +19,7 @@ __global__ void __launch_bounds__(kThreads)
 k_fwt_fwd_str(const __grid_constant__ Taps taps, const FwtFwdStrArgs a) {
   extern __shared__ double smem[];
   const int c = threadIdx.x % kC, g0 = threadIdx.x / kC;
+  const int kGroupsPerPass = blockDim.x / kC;
   const int m = a.m, h = a.h;
   int64_t b = blockIdx.x;
   const int cb = int(b % a.cblocks); b /= a.cblocks;
@@ -105,6 +106,7 @@ __global__ void __launch_bounds__(kThreads)
 k_fwt_rev_str(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevStrArgs a) {
   extern __shared__ double smem[];
   const int c = threadIdx.x % kC, g0 = threadIdx.x / kC;
+  const int kGroupsPerPass = blockDim.x / kC;
   const int m = a.m, h0 = a.h0;
   int64_t b = blockIdx.x;
   const int cb = int(b % a.cblocks); b /= a.cblocks;
@@ -225,7 +227,7 @@ static cudaError_t launch_fwd_L(jwc_ctx* ctx, const Taps& taps, FwtFwdStrArgs a,
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
   }
-  kern<<<int(grid), kThreads, smem, ctx->stream>>>(taps, a);
+  kern<<<int(grid), ctx->str_threads, smem, ctx->stream>>>(taps, a);
   ctx->launches++;
   return cudaGetLastError();
 }
@@ -281,7 +283,7 @@ static cudaError_t launch_rev_L(jwc_ctx* ctx, const Taps& taps, FwtRevStrArgs a,
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
   }
-  kern<<<int(grid), kThreads, smem, ctx->stream>>>(taps, a);
+  kern<<<int(grid), ctx->str_threads, smem, ctx->stream>>>(taps, a);
   ctx->launches++;
   return cudaGetLastError();
 }

@@ -43,6 +43,16 @@ static cudaError_t copy_through(jwc_ctx* ctx, const double* in, double* out, int
     if (e__ != cudaSuccess) return e__;     \
   } while (0)
 
+// Lines per CTA in resident mode: as many as fit a shared-memory budget that keeps ~4 CTAs per SM,
+// so short lines (the tail of every full-depth transform) still fill the CTA's threads.
+static int resident_lines(int h, int bytes_per_sample_x10) {
+  const int64_t per_line = int64_t(h) * bytes_per_sample_x10 / 10 + 64;
+  int64_t g = (48 * 1024) / per_line;
+  if (g < 1) g = 1;
+  if (g > 64) g = 64;
+  return int(g);
+}
+
 // ---- FWT ---------------------------------------------------------------------------------------
 
 static bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; }
@@ -204,7 +214,7 @@ static cudaError_t fwt_forward(jwc_ctx* ctx, const WaveletRec& w, const double* 
     const Pass& p = passes[i];
     const bool last = (i == npass - 1);
     a.h = p.h; a.T = p.T; a.m = p.m;
-    a.G = p.resident ? (cap / p.h > 0 ? cap / p.h : 1) : 1;
+    a.G = p.resident ? resident_lines(p.h, 150) : 1;   // fwd: (h/2 + h/4) double2, padded 1.25
     a.dstA = last ? out : S[(i + 1) & 1];
     a.dstA_os = last ? n : (p.h >> p.m);
     JWC_TRY(launch_fwt_fwd(ctx, w.L, w.de, a, p.resident));
@@ -290,7 +300,7 @@ static cudaError_t fwt_reverse(jwc_ctx* ctx, const WaveletRec& w, const double* 
     const bool last = (p.h0 == n);
     a.h0 = p.h0; a.m = p.m; a.dbg = ctx->dbg;
     a.T = (p.resident || p.h0 < ctx->rev_tile) ? p.h0 : ctx->rev_tile;
-    a.G = p.resident ? (cap / p.h0 > 0 ? cap / p.h0 : 1) : 1;
+    a.G = p.resident ? resident_lines(p.h0, 175) : 1;  // rev: (h + h/2 + h/4) samples, padded 1.25
     a.dst = last ? out : S[i & 1];
     a.dst_os = last ? n : p.h0;
     JWC_TRY(launch_fwt_rev(ctx, w.L, w.re, a, p.resident));
@@ -373,7 +383,7 @@ static cudaError_t wpt_forward(jwc_ctx* ctx, const WaveletRec& w, const double* 
     a.lines = outer * (n / p.h);
     a.h = p.h; a.m = p.m;
     a.T = (p.resident || p.h < ctx->wpt_tile) ? p.h : ctx->wpt_tile;
-    a.G = p.resident ? ctx->res_cap / p.h : 1;
+    a.G = p.resident ? resident_lines(p.h, 200) : 1;   // wpt: two full line buffers, padded 1.25
     JWC_TRY(launch_wpt_fwd(ctx, w.L, w.de, a, p.resident));
     src = a.dst;
   }
@@ -419,7 +429,7 @@ static cudaError_t wpt_reverse(jwc_ctx* ctx, const WaveletRec& w, const double* 
     a.lines = outer * (n / p.h0);
     a.h0 = p.h0; a.m = p.m;
     a.T = (p.resident || p.h0 < ctx->wpt_tile) ? p.h0 : ctx->wpt_tile;
-    a.G = p.resident ? ctx->res_cap / p.h0 : 1;
+    a.G = p.resident ? resident_lines(p.h0, 200) : 1;
     JWC_TRY(launch_wpt_rev(ctx, w.L, w.re, a, p.resident));
     src = a.dst;
   }

@@ -13,7 +13,6 @@ namespace jwc {
 
 constexpr int kC = 8;            // columns per CTA
 constexpr int kSR = 4;           // outputs (forward) / slots (reverse) per thread and step
-constexpr int kGroupsPerPass = kThreads / kC;
 
 __device__ __forceinline__ int srow(int r) { return r ^ ((r >> 3) & 1); }
 __device__ __forceinline__ double& sat(double* buf, int r, int c) { return buf[srow(r) * kC + c]; }
@@ -22,7 +21,7 @@ __device__ __forceinline__ const double& sat(const double* buf, int r, int c) { 
 // stage `rows` sample rows of kC columns: row r <- global sample ((first + r) mod width) of the line
 // block starting at `gsrc` (sample stride `inner` doubles); 16 bytes per cp.async
 __device__ __forceinline__ void stage_rows(double* buf, const double* gsrc, int64_t inner, int first, int rows, int wmask) {
-  for (int it = threadIdx.x; it < rows * (kC / 2); it += kThreads) {
+  for (int it = threadIdx.x; it < rows * (kC / 2); it += blockDim.x) {
     const int r = it / (kC / 2), c2 = it - r * (kC / 2);
     cp_async16(&buf[srow(r) * kC + 2 * c2], gsrc + int64_t((first + r) & wmask) * inner + 2 * c2);
   }
