@@ -7,6 +7,10 @@
 // Here a CTA owns kC = 8 adjacent lines (64 contiguous bytes per sample) and a run of samples
 // along the axis, staged as [sample][8] in shared memory; no gather, no transpose, and `m` levels
 // per launch.  Tile / resident modes and halo arithmetic are those of jwc_fwt_fwd.cu / jwc_fwt_rev.cu.
+#include <cuda.h>
+
+#include <cstring>
+
 #include "jwc_kernels.cuh"
 #include "jwc_strided.cuh"
 
@@ -14,10 +18,37 @@ namespace jwc {
 
 // ================================ forward ======================================================
 
-template <int L, bool RESIDENT>
+// Stage `rows` level-0 rows (first global row `y0` of the tensor, column x0) with TMA: whole boxes of
+// kBoxRows rows; a tile that runs past the end of its line wraps to the line's first row (the
+// periodic halo), and the wrap point is always a multiple of the box height.
+__device__ __forceinline__ void tma_stage(double* buf, uint64_t* bar, const void* tmap, int x0, int64_t line_row0,
+                                          int first, int rows, int h) {
+  if (threadIdx.x == 0) {
+    const int boxes = (rows + kBoxRows - 1) / kBoxRows;
+    mbar_expect_tx(bar, unsigned(boxes) * kBoxRows * kC * sizeof(double));
+    for (int b = 0; b < boxes; ++b) {
+      const int s = (first + b * kBoxRows) & (h - 1);   // sample index inside the line
+      tma_load_box(buf + b * kBoxRows * kC, tmap, x0, int(line_row0 + s), bar);
+    }
+  }
+  mbar_wait(bar, 0);
+}
+
+template <int L, bool TMA0, class Store>
+__device__ __forceinline__ void fwd_str_level_tile(const Taps& taps, const double* cur, int groups, int c, int g0,
+                                                   int gpp, Store store) {
+  for (int g = g0; g < groups; g += gpp) {
+    double lo[kSR], hi[kSR];
+    if constexpr (TMA0) fwd_run<L, kSR>(taps, [&](int s) { return tma_at(cur, 2 * kSR * g + s, c); }, lo, hi);
+    else fwd_run<L, kSR>(taps, [&](int s) { return sat(cur, 2 * kSR * g + s, c); }, lo, hi);
+    store(g, lo, hi);
+  }
+}
+
+template <int L, bool RESIDENT, bool TMA>
 __global__ void __launch_bounds__(kThreads)
-k_fwt_fwd_str(const __grid_constant__ Taps taps, const FwtFwdStrArgs a) {
-  extern __shared__ double smem[];
+k_fwt_fwd_str(const __grid_constant__ Taps taps, const FwtFwdStrArgs a, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(1024) double smem[];
   const int c = threadIdx.x % kC, g0 = threadIdx.x / kC;
   const int kGroupsPerPass = blockDim.x / kC;
   const int m = a.m, h = a.h;
@@ -31,21 +62,29 @@ k_fwt_fwd_str(const __grid_constant__ Taps taps, const FwtFwdStrArgs a) {
   double* gA = a.dstA + o * a.dstA_os + cb * kC + c;
   double* cur = smem;
   double* nxt = smem + a.rows0 * kC;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (a.rows0 + a.rows1) * kC);
+  if constexpr (TMA) {
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    __syncthreads();
+  }
 
   if constexpr (!RESIDENT) {
     const int T = a.T;
-    stage_rows(cur, src, inner, tile * T, T + ((1 << m) - 1) * (L - 2), h - 1);
-    cp_async_wait_all();
-    __syncthreads();
+    const int n0 = T + ((1 << m) - 1) * (L - 2);
+    if constexpr (TMA) {
+      tma_stage(cur, bar, &tmap, cb * kC, o * a.rows_per_o, tile * T, n0, h);
+    } else {
+      stage_rows(cur, src, inner, tile * T, n0, h - 1);
+      cp_async_wait_all();
+      __syncthreads();
+    }
     for (int k = 1; k <= m; ++k) {
       const int n_det = T >> k;
       const int n_out = n_det + ((1 << (m - k)) - 1) * (L - 2);
       const int groups = (n_out + kSR - 1) / kSR;
       const bool last = (k == m);
       const int64_t rowD = (h >> k) + tile * n_det, rowA = tile * n_det;
-      for (int g = g0; g < groups; g += kGroupsPerPass) {
-        double lo[kSR], hi[kSR];
-        fwd_run<L, kSR>(taps, [&](int s) { return sat(cur, 2 * kSR * g + s, c); }, lo, hi);
+      auto store = [&](int g, const double (&lo)[kSR], const double (&hi)[kSR]) {
         const bool keep = kSR * g < n_det;
 #pragma unroll
         for (int r = 0; r < kSR; ++r) {
@@ -53,22 +92,30 @@ k_fwt_fwd_str(const __grid_constant__ Taps taps, const FwtFwdStrArgs a) {
           else if (keep) gA[(rowA + kSR * g + r) * inner] = lo[r];
           if (keep) gD[(rowD + kSR * g + r) * inner] = hi[r];
         }
-      }
+      };
+      if (TMA && k == 1) fwd_str_level_tile<L, TMA>(taps, cur, groups, c, g0, kGroupsPerPass, store);
+      else fwd_str_level_tile<L, false>(taps, cur, groups, c, g0, kGroupsPerPass, store);
       __syncthreads();
       double* t = cur; cur = nxt; nxt = t;
     }
   } else {
-    stage_rows(cur, src, inner, 0, h, h - 1);
-    cp_async_wait_all();
-    __syncthreads();
+    if constexpr (TMA) {
+      tma_stage(cur, bar, &tmap, cb * kC, o * a.rows_per_o, 0, h, h);
+    } else {
+      stage_rows(cur, src, inner, 0, h, h - 1);
+      cp_async_wait_all();
+      __syncthreads();
+    }
     for (int k = 1; k <= m; ++k) {
       const int h_in = h >> (k - 1), h_out = h_in >> 1;
       const int mask = h_in - 1;
       const bool last = (k == m);
+      const bool tma0 = TMA && k == 1;
       if (h_out >= kSR) {
         for (int g = g0; g < h_out / kSR; g += kGroupsPerPass) {
           double lo[kSR], hi[kSR];
-          fwd_run<L, kSR>(taps, [&](int s) { return sat(cur, (2 * kSR * g + s) & mask, c); }, lo, hi);
+          if (tma0) fwd_run<L, kSR>(taps, [&](int s) { return tma_at(cur, (2 * kSR * g + s) & mask, c); }, lo, hi);
+          else fwd_run<L, kSR>(taps, [&](int s) { return sat(cur, (2 * kSR * g + s) & mask, c); }, lo, hi);
 #pragma unroll
           for (int r = 0; r < kSR; ++r) {
             if (!last) sat(nxt, kSR * g + r, c) = lo[r];
@@ -82,7 +129,7 @@ k_fwt_fwd_str(const __grid_constant__ Taps taps, const FwtFwdStrArgs a) {
           double lo = 0.0, hi = 0.0;
 #pragma unroll
           for (int j = 0; j < L; ++j) {
-            const double v = sat(cur, (2 * i + j) & mask, c);
+            const double v = sat(cur, (2 * i + j) & mask, c);   // never the TMA buffer: h >= kBoxRows there
             lo = fma(v, taps.lo[j], lo);
             hi = fma(v, hi_tap<L>(taps, j), hi);
           }
@@ -203,31 +250,69 @@ int fwt_str_tile_levels(int L, int T) {
   return m;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// 2-D map of the source as [rows][inner] doubles, box {8 columns, kBoxRows rows}, dense in shared memory
+static bool make_tmap(CUtensorMap* map, const double* base, int64_t rows, int64_t inner) {
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc || (reinterpret_cast<uintptr_t>(base) & 15) || (inner * sizeof(double)) % 16) return false;
+  const cuuint64_t dims[2] = {cuuint64_t(inner), cuuint64_t(rows)};
+  const cuuint64_t strides[1] = {cuuint64_t(inner) * sizeof(double)};
+  const cuuint32_t box[2] = {kC, kBoxRows};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int L>
 static cudaError_t launch_fwd_L(jwc_ctx* ctx, const Taps& taps, FwtFwdStrArgs a, bool resident) {
   if (a.inner % kC) return cudaErrorInvalidValue;
   a.cblocks = int(a.inner / kC);
   int64_t grid;
+  // TMA needs whole boxes: tiles and resident lines of at least kBoxRows rows
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  a.rows_per_o = a.src_os / a.inner;
+  bool tma = ctx->str_tma && (resident ? a.h : a.T) >= kBoxRows && a.src_os % a.inner == 0 &&
+             make_tmap(&tmap, a.src, a.outer * a.rows_per_o, a.inner);
   if (!resident) {
     if ((a.T >> a.m) < kSR) return cudaErrorInvalidValue;
-    a.rows0 = a.T + ((1 << a.m) - 1) * (L - 2) + 8;
+    const int n0 = a.T + ((1 << a.m) - 1) * (L - 2);
+    a.rows0 = tma ? (n0 + kBoxRows - 1) / kBoxRows * kBoxRows : n0 + 8;   // whole boxes land in shared memory
     a.rows1 = (a.T >> 1) + ((1 << (a.m - 1)) - 1) * (L - 2) + 8;
     a.tiles_per_line = a.h / a.T;
     grid = a.outer * a.tiles_per_line * a.cblocks;
   } else {
-    a.rows0 = a.h + 2;
+    a.rows0 = tma ? (a.h + kBoxRows - 1) / kBoxRows * kBoxRows : a.h + 2;
     a.rows1 = max(2, a.h / 2) + 2;
     a.tiles_per_line = 1;
     grid = a.outer * a.cblocks;
   }
-  const size_t smem = size_t(a.rows0 + a.rows1) * kC * sizeof(double);
+  const size_t smem = size_t(a.rows0 + a.rows1) * kC * sizeof(double) + 16;  // + the mbarrier
   if (grid > 0x7fffffff) return cudaErrorInvalidConfiguration;
-  auto kern = resident ? k_fwt_fwd_str<L, true> : k_fwt_fwd_str<L, false>;
+  void (*kern)(const Taps, const FwtFwdStrArgs, const CUtensorMap) =
+      resident ? (tma ? k_fwt_fwd_str<L, true, true> : k_fwt_fwd_str<L, true, false>)
+               : (tma ? k_fwt_fwd_str<L, false, true> : k_fwt_fwd_str<L, false, false>);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
   }
-  kern<<<int(grid), ctx->str_threads, smem, ctx->stream>>>(taps, a);
+  kern<<<int(grid), ctx->str_threads, smem, ctx->stream>>>(taps, a, tmap);
   ctx->launches++;
   return cudaGetLastError();
 }

@@ -48,6 +48,7 @@ struct FwtFwdStrArgs {
   int64_t outer, inner;
   int h, m, T;
   int tiles_per_line, cblocks, rows0, rows1;  // filled in by the launcher
+  int64_t rows_per_o;                         // tensor rows between consecutive `outer` slices (TMA path)
 };
 int fwt_str_tile_levels(int L, int T);
 cudaError_t launch_fwt_fwd_str(jwc_ctx* ctx, int L, const Taps& taps, const FwtFwdStrArgs& a, bool resident);

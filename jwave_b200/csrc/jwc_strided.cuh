@@ -27,6 +27,50 @@ __device__ __forceinline__ void stage_rows(double* buf, const double* gsrc, int6
   }
 }
 
+// ---- TMA staging (Blackwell / Hopper bulk tensor copy) -------------------------------------------
+// The level-0 tile of the strided kernels can be staged as 2-D boxes {8 columns, kBoxRows rows} of
+// the matrix [rows][inner]: one elected thread issues cp.async.bulk.tensor.2d per box, completion is
+// counted on an mbarrier.  The box lands DENSE ([row][8], 64-byte rows, SWIZZLE_NONE).  Measured on
+// B200 (tools/tma_decode.py): with SWIZZLE_128B a 64-byte box row occupies a whole 128-byte line
+// (half the staging buffer wasted), and SWIZZLE_64B only permutes chunks inside a row - neither
+// gives the row-pair swap of srow(), so the level-1 window reads of a TMA-staged tile pay 4
+// instead of 2 wavefronts per LDS.64.  The copy engine still wins (no per-16-byte address
+// arithmetic, one instruction per 8 KB): +7 % on the 8192^2 Daubechies20 column pass, so TMA is the
+// default where whole boxes fit (tiles / lines of >= kBoxRows rows); cp.async + srow() otherwise.
+constexpr int kBoxRows = 128;
+
+__device__ __forceinline__ const double& tma_at(const double* buf, int r, int c) { return buf[r * kC + c]; }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(bar));
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(bar));
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned phase) {
+  const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(bar));
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(a), "r"(phase) : "memory");
+}
+// one box: columns [x, x + 8), rows [y, y + kBoxRows) of the tensor -> smem_dst (128-byte aligned)
+__device__ __forceinline__ void tma_load_box(void* smem_dst, const void* tmap, int x, int y, uint64_t* bar) {
+  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  const unsigned b = static_cast<unsigned>(__cvta_generic_to_shared(bar));
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(d), "l"(tmap), "r"(x), "r"(y), "r"(b) : "memory");
+}
+
 // forward: outputs i = R g .. R g + R - 1 of one column; x(s) = input sample 2 R g + s,
 // s = 0 .. 2R + L - 3 (Wavelet.java:244-254, j ascending, FMA-contracted)
 template <int L, int R, class X>
