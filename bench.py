@@ -271,6 +271,7 @@ def main():
     launches0 = dev.launch_count()
     if sampler:
         sampler.start()
+    dev.ctx.profile(True)  # event pair around every kernel launch, read after the timed region
     barrier()
     ev[0].record()
     for i in range(args.steps):
@@ -281,6 +282,8 @@ def main():
     ev[1].record()
     barrier()
     clocks = sampler.stop() if sampler else None
+    prof = dev.ctx.profile_report()
+    dev.ctx.profile(False)
     launches = dev.launch_count() - launches0
     ms = ev[0].elapsed_time(ev[1])
     fwd_ms = statistics.mean(a.elapsed_time(b) for a, b in fwd_ev)
@@ -293,25 +296,46 @@ def main():
     samples = x.numel()  # per GPU
     value = 2.0 * samples * world / (ms_per_step * 1e-3) * 1e-9
 
-    # ---- roofline of the dominant kernel (forward pass) ---------------------------------------
+    # ---- roofline of the dominant kernel ------------------------------------------------------------
+    # Per-kernel CUDA-event times from the timed region (jwc_profile_*).  Algorithmic work of one
+    # launch: 16 B per sample it transforms (one read + one write), and
+    # direct-form flops 4 L (1 - 2^-m) per sample for m fused FWT levels, 2 L m for m WPT levels.
     hbm_peak, peak_src = peaks()
-    bytes_per_sample = 16.0 * dims  # one read + one write of every sample per axis pass
+    bytes_per_sample = 16.0 * dims
     flops_per_sample = 2.0 * L * level if kind == "wpt" else dims * (2.0 * L * 2.0 * (1.0 - 0.5 ** level))
+    prof_total = sum(r[2] for r in prof) or 1.0
+    kernels = []
+    for name, count, total_ms, units, lv in prof:
+        t = total_ms / count * 1e-3
+        k_bytes = 16.0 * units
+        k_flops = units * (2.0 * L * lv if "wpt" in name else 4.0 * L * (1.0 - 0.5 ** lv))
+        kernels.append({"kernel": f"{name}<{L}>", "launches": count, "avg_ms": total_ms / count,
+                        "share": total_ms / prof_total, "samples_per_launch": units, "levels": lv,
+                        "hbm_frac": k_bytes / t * 1e-9 / hbm_peak, "fp64_frac": k_flops / t * 1e-12 / FP64_PEAK_TFLOPS})
+    kernels.sort(key=lambda k: -k["share"])
+    dom = kernels[0]
+    t_dom = dom["avg_ms"] * 1e-3
+    if dom["hbm_frac"] >= dom["fp64_frac"]:
+        achieved = 16.0 * dom["samples_per_launch"] / t_dom * 1e-9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "peak_source": peak_src}
+    else:
+        achieved = dom["fp64_frac"] * FP64_PEAK_TFLOPS
+        roof = {"bound": "fp64", "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+                "frac": dom["fp64_frac"], "peak_source": "measured DFMA peak (tools/microbench.cu, profiles/r01_microbench.txt)"}
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from ncu --set full captures
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(f"{args.workload}:{dom['kernel']}")
     t_hbm = samples * bytes_per_sample / (hbm_peak * 1e9)
     t_fp64 = samples * flops_per_sample / (FP64_PEAK_TFLOPS * 1e12)
-    if t_hbm >= t_fp64:
-        achieved = samples * bytes_per_sample / (fwd_ms * 1e-3) * 1e-9
-        roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak}
-    else:
-        achieved = samples * flops_per_sample / (fwd_ms * 1e-3) * 1e-12
-        roof = {"bound": "fp64", "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
-                "frac": achieved / FP64_PEAK_TFLOPS}
-    roof.update({"traffic": None, "kernel": f"forward pass ({'k_wpt_fwd' if kind == 'wpt' else 'k_fwt_fwd'}<{L}>, all launches)",
-                 "peak_source": peak_src if roof["bound"] == "hbm" else "measured DFMA peak (tools/microbench.cu)",
+    t_roof = max(t_hbm, t_fp64)
+    roof.update({"traffic": traffic, "kernel": dom["kernel"], "kernel_share_of_step": dom["share"],
+                 "kernel_avg_ms": dom["avg_ms"], "kernels": kernels,
                  "forward_ms": fwd_ms, "reverse_ms": rev_ms,
                  "algorithmic_bytes_per_sample": bytes_per_sample, "algorithmic_flops_per_sample": flops_per_sample,
-                 "reverse_frac": (samples * bytes_per_sample / (rev_ms * 1e-3) * 1e-9 / hbm_peak) if t_hbm >= t_fp64
-                 else (samples * flops_per_sample / (rev_ms * 1e-3) * 1e-12 / FP64_PEAK_TFLOPS)})
+                 "direction_roofline": "hbm" if t_hbm >= t_fp64 else "fp64",
+                 "forward_frac": t_roof / (fwd_ms * 1e-3), "reverse_frac": t_roof / (rev_ms * 1e-3)})
 
     # ---- e2e: the same step through the host-buffer C ABI ------------------------------------
     e2e = None

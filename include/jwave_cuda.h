@@ -74,6 +74,13 @@ int jwc_sync(jwc_ctx* ctx);
 /* Number of kernels this context has launched so far. */
 int64_t jwc_launch_count(const jwc_ctx* ctx);
 
+/* Per-launch timing for benchmarks: while enabled, every kernel launch is bracketed by a CUDA
+ * event pair on the launching stream.  jwc_profile_report waits for the recorded launches and
+ * writes one text line per kernel, "label,launches,total_ms,samples_per_launch,levels", then clears the
+ * records.  Off by default (no events are created). */
+int jwc_profile_enable(jwc_ctx* ctx, int on);
+int jwc_profile_report(jwc_ctx* ctx, char* buf, size_t size);
+
 /* Register a wavelet from the four arrays returned by the reference's getters
  * (Wavelet.getScalingDeComposition() ... getWaveletReConstruction(), Wavelet.java:178-219), so
  * the device filters are bit-identical to the JVM's.  L must be even, 2 <= L <= JWC_MAX_TAPS.

@@ -28,6 +28,8 @@ SIGNATURES = {
     "jwc_reset_stream": (_int, [_vp]),
     "jwc_sync": (_int, [_vp]),
     "jwc_launch_count": (_i64, [_vp]),
+    "jwc_profile_enable": (_int, [_vp, _int]),
+    "jwc_profile_report": (_int, [_vp, C.c_char_p, C.c_size_t]),
     "jwc_set_wavelet": (_int, [_vp, _int, _dp, _dp, _dp, _dp, C.POINTER(_int)]),
     "jwc_fwt1d": (_int, [_vp, _int, _int, _vp, _vp, _i64, _int, _int]),
     "jwc_wpt1d": (_int, [_vp, _int, _int, _vp, _vp, _i64, _int, _int]),

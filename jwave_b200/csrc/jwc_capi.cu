@@ -28,6 +28,8 @@ static int fail(jwc_ctx* ctx, int status, const char* msg) {
   return status;
 }
 
+static void prof_clear(jwc_ctx* ctx);
+
 extern "C" int jwc_version(void) { return JWC_VERSION; }
 
 extern "C" int jwc_create(jwc_ctx** out, int device) {
@@ -121,6 +123,7 @@ extern "C" int jwc_destroy(jwc_ctx* ctx) {
   if (!ctx) return JWC_ERR_ARG;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
+  prof_clear(ctx);
   for (auto& s : ctx->scratch) free_scratch(s);
   for (int i = 0; i < 2; ++i) {
     free_scratch(ctx->stage_in[i]);
@@ -164,6 +167,55 @@ extern "C" int jwc_sync(jwc_ctx* ctx) {
 }
 
 extern "C" int64_t jwc_launch_count(const jwc_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+static void prof_clear(jwc_ctx* ctx) {
+  for (auto& r : ctx->prof) {
+    cudaEventDestroy(r.beg);
+    cudaEventDestroy(r.end);
+  }
+  ctx->prof.clear();
+}
+
+extern "C" int jwc_profile_enable(jwc_ctx* ctx, int on) {
+  if (!ctx) return JWC_ERR_ARG;
+  JWC_CUDA(ctx, cudaSetDevice(ctx->device));
+  prof_clear(ctx);
+  ctx->prof_on = on != 0;
+  return JWC_OK;
+}
+
+// Text report, one line per kernel label: "name,launches,total_ms,samples_per_launch,levels".  Waits for the
+// recorded launches, then clears the records.
+extern "C" int jwc_profile_report(jwc_ctx* ctx, char* buf, size_t size) {
+  if (!ctx || !buf || size == 0) return JWC_ERR_ARG;
+  JWC_CUDA(ctx, cudaSetDevice(ctx->device));
+  struct Acc { const char* name; int n; double ms, units; int levels; };
+  std::vector<Acc> acc;
+  for (auto& r : ctx->prof) {
+    JWC_CUDA(ctx, cudaEventSynchronize(r.end));
+    float ms = 0.f;
+    JWC_CUDA(ctx, cudaEventElapsedTime(&ms, r.beg, r.end));
+    Acc* hit = nullptr;
+    for (auto& a : acc)
+      if (!strcmp(a.name, r.name) && a.units == r.units && a.levels == r.levels) hit = &a;
+    if (!hit) {
+      acc.push_back({r.name, 0, 0.0, r.units, r.levels});
+      hit = &acc.back();
+    }
+    hit->n++;
+    hit->ms += ms;
+  }
+  std::string out;
+  char line[256];
+  for (auto& a : acc) {
+    snprintf(line, sizeof(line), "%s,%d,%.6f,%.0f,%d\n", a.name, a.n, a.ms, a.units, a.levels);
+    out += line;
+  }
+  prof_clear(ctx);
+  if (out.size() + 1 > size) return fail(ctx, JWC_ERR_ARG, "jwc_profile_report: buffer too small");
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return JWC_OK;
+}
 
 extern "C" int jwc_set_wavelet(jwc_ctx* ctx, int L, const double* sDe, const double* wDe,
                                const double* sRe, const double* wRe, int* wid) {

@@ -45,9 +45,18 @@ template <int L, int R, class Win>
 __device__ __forceinline__ void fwd_stepR(const Taps& taps, Win win, double (&lo)[R], double (&hi)[R]) {
 #pragma unroll
   for (int r = 0; r < R; ++r) lo[r] = hi[r] = 0.0;
+  constexpr int W = L / 2 + R - 1;
+  constexpr bool kPrefetch = (W <= 8);  // short filters: whole window in registers before the FMAs
+  double2 wv[kPrefetch ? W : 1];
+  if constexpr (kPrefetch) {
 #pragma unroll
-  for (int q = 0; q < L / 2 + R - 1; ++q) {
-    const double2 v = win(q);
+    for (int q = 0; q < W; ++q) wv[q] = win(q);
+  }
+#pragma unroll
+  for (int q = 0; q < W; ++q) {
+    double2 v;
+    if constexpr (kPrefetch) v = wv[q];
+    else v = win(q);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const int jj = q - r;

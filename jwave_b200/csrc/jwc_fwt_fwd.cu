@@ -160,7 +160,9 @@ static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, FwtFwdArgs a, bool r
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
   }
+  prof_begin(ctx, resident ? "k_fwt_fwd:resident" : "k_fwt_fwd:tile", double(a.lines) * a.h, a.m);
   kern<<<grid, resident ? ctx->res_threads : ctx->fwd_threads, smem, ctx->stream>>>(taps, a);
+  prof_end(ctx);
   ctx->launches++;
   return cudaGetLastError();
 }

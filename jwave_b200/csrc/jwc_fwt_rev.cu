@@ -28,9 +28,19 @@ __device__ __forceinline__ void rev_step(const Taps& taps, A2 a2, D2 d2, double 
 #pragma unroll
   for (int r = 0; r < 2 * RS; ++r) t[r] = 0.0;
   constexpr int W = (L / 2) / 2 + RS / 2;
+  // short filters: fetch the whole window first, so the LDS latency is paid once per group instead of
+  // once per window step (the stall samples of the streaming form sat on short-scoreboard waits)
+  constexpr bool kPrefetch = (W <= 6);
+  double2 wa[kPrefetch ? W : 1], wd[kPrefetch ? W : 1];
+  if constexpr (kPrefetch) {
+#pragma unroll
+    for (int w = 0; w < W; ++w) { wa[w] = a2(w); wd[w] = d2(w); }
+  }
 #pragma unroll
   for (int w = 0; w < W; ++w) {
-    const double2 av = a2(w), dv = d2(w);
+    double2 av, dv;
+    if constexpr (kPrefetch) { av = wa[w]; dv = wd[w]; }
+    else { av = a2(w); dv = d2(w); }
 #pragma unroll
     for (int pp = 0; pp < RS; ++pp) {
       const int qy = pp - (RS - 1) + 2 * w;  // .y is slot RS g' + RS - 1 - 2w
@@ -236,7 +246,9 @@ static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, FwtRevArgs a, bool r
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
   }
+  prof_begin(ctx, resident ? "k_fwt_rev:resident" : "k_fwt_rev:tile", double(a.lines) * a.h0, a.m);
   kern<<<grid, resident ? ctx->res_threads : ctx->rev_threads, smem, ctx->stream>>>(taps, a);
+  prof_end(ctx);
   ctx->launches++;
   return cudaGetLastError();
 }

@@ -312,7 +312,9 @@ static cudaError_t launch_fwd_L(jwc_ctx* ctx, const Taps& taps, FwtFwdStrArgs a,
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
   }
+  prof_begin(ctx, resident ? "k_fwt_fwd_str:resident" : "k_fwt_fwd_str:tile", double(a.outer) * a.h * a.inner, a.m);
   kern<<<int(grid), ctx->str_threads, smem, ctx->stream>>>(taps, a, tmap);
+  prof_end(ctx);
   ctx->launches++;
   return cudaGetLastError();
 }
@@ -368,7 +370,9 @@ static cudaError_t launch_rev_L(jwc_ctx* ctx, const Taps& taps, FwtRevStrArgs a,
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
   }
+  prof_begin(ctx, resident ? "k_fwt_rev_str:resident" : "k_fwt_rev_str:tile", double(a.outer) * a.h0 * a.inner, a.m);
   kern<<<int(grid), ctx->str_threads, smem, ctx->stream>>>(taps, a);
+  prof_end(ctx);
   ctx->launches++;
   return cudaGetLastError();
 }

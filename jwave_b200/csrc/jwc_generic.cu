@@ -74,7 +74,9 @@ static int grid_for(const jwc_ctx* ctx, int64_t total) {
 cudaError_t launch_fwd_level_generic(jwc_ctx* ctx, int L, const Taps& taps, const FwdLevelArgs& a) {
   const int64_t total = a.outer * a.half * a.inner;
   if (total <= 0) return cudaSuccess;
+  prof_begin(ctx, "k_fwd_level_generic", 2.0 * double(total), 1);
   k_fwd_level_generic<<<grid_for(ctx, total), 256, 0, ctx->stream>>>(taps, L, a);
+  prof_end(ctx);
   ctx->launches++;
   return cudaGetLastError();
 }
@@ -82,7 +84,9 @@ cudaError_t launch_fwd_level_generic(jwc_ctx* ctx, int L, const Taps& taps, cons
 cudaError_t launch_rev_level_generic(jwc_ctx* ctx, int L, const Taps& taps, const RevLevelArgs& a) {
   const int64_t total = a.outer * a.half * a.inner;
   if (total <= 0) return cudaSuccess;
+  prof_begin(ctx, "k_rev_level_generic", 2.0 * double(total), 1);
   k_rev_level_generic<<<grid_for(ctx, total), 256, 0, ctx->stream>>>(taps, L, a);
+  prof_end(ctx);
   ctx->launches++;
   return cudaGetLastError();
 }

@@ -35,6 +35,15 @@ struct WaveletRec {
   Taps re;  // reconstruction: _scalingReCon / _waveletReCon
 };
 
+// Optional per-launch timing (jwc_profile_enable): an event pair around every kernel launch on the
+// launching stream, summed per kernel label when the report is read.
+struct ProfRec {
+  const char* name;
+  cudaEvent_t beg, end;
+  double units;  // samples the launch transforms (its algorithmic work, for roofline arithmetic)
+  int levels;    // decomposition levels fused in the launch
+};
+
 struct Scratch {
   void* ptr = nullptr;
   size_t bytes = 0;
@@ -52,6 +61,8 @@ struct jwc_ctx {
   std::vector<jwc::WaveletRec> wavelets;
   std::string err;
   int64_t launches = 0;
+  bool prof_on = false;
+  std::vector<jwc::ProfRec> prof;
   jwc::Scratch scratch[4];      // [0],[1]: level ping-pong; [2]: axis ping-pong; [3]: alias guard
   jwc::Scratch stage_in[2], stage_out[2];
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
@@ -63,6 +74,20 @@ struct jwc_ctx {
 };
 
 namespace jwc {
+
+// bracket a kernel launch with profile events (no-ops unless profiling is on)
+inline void prof_begin(jwc_ctx* ctx, const char* name, double units, int levels) {
+  if (!ctx->prof_on) return;
+  ProfRec r{name, nullptr, nullptr, units, levels};
+  cudaEventCreate(&r.beg);
+  cudaEventCreate(&r.end);
+  cudaEventRecord(r.beg, ctx->stream);
+  ctx->prof.push_back(r);
+}
+inline void prof_end(jwc_ctx* ctx) {
+  if (!ctx->prof_on || ctx->prof.empty()) return;
+  cudaEventRecord(ctx->prof.back().end, ctx->stream);
+}
 
 // ---- geometry of one level over a set of lines ---------------------------------------------
 // A "line" is the 1-D sequence the transform runs along.  Element s of line (o, c) lives at

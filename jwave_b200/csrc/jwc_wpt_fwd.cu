@@ -221,7 +221,9 @@ static cudaError_t launch_LR(jwc_ctx* ctx, const Taps& taps, WptFwdArgs a, bool 
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
   }
+  prof_begin(ctx, resident ? "k_wpt_fwd:resident" : "k_wpt_fwd:tile", double(a.lines) * a.h, a.m);
   kern<<<int(grid), ctx->wpt_threads, smem, ctx->stream>>>(taps, a);
+  prof_end(ctx);
   ctx->launches++;
   return cudaGetLastError();
 }

@@ -246,7 +246,9 @@ static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, WptRevArgs a, bool r
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
   }
+  prof_begin(ctx, resident ? "k_wpt_rev:resident" : "k_wpt_rev:tile", double(a.lines) * a.h0, a.m);
   kern<<<int(grid), ctx->wpt_threads, smem, ctx->stream>>>(taps, a);
+  prof_end(ctx);
   ctx->launches++;
   return cudaGetLastError();
 }

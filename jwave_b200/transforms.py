@@ -92,6 +92,20 @@ class CudaContext:
     def launch_count(self):
         return int(self._lib.jwc_launch_count(self.handle))
 
+    def profile(self, on):
+        """Bracket every kernel launch with CUDA events (jwc_profile_enable)."""
+        self.check(self._lib.jwc_profile_enable(self.handle, 1 if on else 0), "jwc_profile_enable")
+
+    def profile_report(self):
+        """[(label, launches, total_ms, samples_per_launch, levels)] since profiling was enabled / last read."""
+        buf = C.create_string_buffer(1 << 16)
+        self.check(self._lib.jwc_profile_report(self.handle, buf, len(buf)), "jwc_profile_report")
+        rows = []
+        for line in buf.value.decode().splitlines():
+            name, n, ms, units, levels = line.split(",")
+            rows.append((name, int(n), float(ms), float(units), int(levels)))
+        return rows
+
     def set_stream(self, cuda_stream):
         """Use the given cudaStream_t handle (0 = CUDA's legacy default stream) for *_dev calls."""
         self.check(self._lib.jwc_set_stream(self.handle, C.c_void_p(cuda_stream or 0)), "jwc_set_stream")

@@ -14,7 +14,7 @@ for t in tunes:
                           "--warmup", "3", "--no-e2e", "--no-cpu"], env=env, capture_output=True, text=True)
     try:
         d = json.loads(out.stdout.strip().splitlines()[-1])
-        print(f"{t or '(default)':45s} fwd {d['forward_gsps']:7.1f} GS/s ({d['roofline']['frac']:.3f})  "
+        print(f"{t or '(default)':45s} fwd {d['forward_gsps']:7.1f} GS/s ({d['roofline']['forward_frac']:.3f})  "
               f"rev {d['reverse_gsps']:7.1f} GS/s ({d['roofline']['reverse_frac']:.3f})  rt_err {d['roundtrip_max_abs_err']:.2e}",
               flush=True)
     except Exception as e:

@@ -9,6 +9,6 @@ for t in sys.argv[2:] or [""]:
                          env=dict(os.environ, JWC_TUNE=t), capture_output=True, text=True)
     try:
         d = json.loads(out.stdout.strip().splitlines()[-1])
-        print(f"{workload} {t or '(default)':45s} fwd {d['forward_gsps']:6.1f} ({d['roofline']['frac']:.3f}) rev {d['reverse_gsps']:6.1f} ({d['roofline']['reverse_frac']:.3f}) launches {d['gpu_launches']}", flush=True)
+        print(f"{workload} {t or '(default)':45s} fwd {d['forward_gsps']:6.1f} ({d['roofline']['forward_frac']:.3f}) rev {d['reverse_gsps']:6.1f} ({d['roofline']['reverse_frac']:.3f}) launches {d['gpu_launches']}", flush=True)
     except Exception as e:
         print(workload, t, "FAILED", e, out.stderr[-400:], flush=True)
