@@ -240,9 +240,10 @@ def main():
 
     def run(direction, src, dst):
         if slab is not None:
-            res = slab.forward(src, n, level, level, level) if direction == _lib.FORWARD else \
-                slab.reverse(src, n, level, level, level)
-            dst.copy_(res)
+            if direction == _lib.FORWARD:
+                slab.forward(src, n, level, level, level, out=dst)
+            else:
+                slab.reverse(src, n, level, level, level, out=dst)
         elif dims == 1:
             dev.transform1d(K, direction, src, level, out=dst)
         elif dims == 2:

@@ -54,16 +54,23 @@ class SlabVolumeTransform:
         dist.all_to_all_single(recv, send, group=self.group)
         return recv.view(W * p, Q // W, R)  # src-major order is i order
 
-    def _to_i_slabs(self, y):
-        """[P][Q/W][R] on every rank -> [P/W][Q][R] on every rank (one all-to-all)."""
+    def _to_i_slabs(self, y, out=None):
+        """[P][Q/W][R] on every rank -> [P/W][Q][R] on every rank (one all-to-all); the unpack copy
+        lands directly in `out` when one is given."""
         W = self.world
         if W == 1:
-            return y
+            if out is None:
+                return y
+            out.copy_(y.view_as(out))
+            return out
         P, q, R = y.shape
         send = y.contiguous()               # chunk d = rows of rank d's i range
         recv = torch.empty_like(send)       # [src][i_local][j_of_src][k]
         dist.all_to_all_single(recv, send, group=self.group)
-        return recv.view(W, P // W, q, R).permute(1, 0, 2, 3).reshape(P // W, W * q, R)
+        if out is None:
+            out = torch.empty(P // W, W * q, R, dtype=y.dtype, device=y.device)
+        out.view(P // W, W, q, R).copy_(recv.view(W, P // W, q, R).permute(1, 0, 2, 3))
+        return out
 
     # -- transforms --------------------------------------------------------------------------------
     def _check(self, x, P):
@@ -72,7 +79,7 @@ class SlabVolumeTransform:
         if x.shape[1] % self.world:
             raise ValueError("Q must be divisible by the number of ranks")
 
-    def forward(self, slab, P, lvlP, lvlQ, lvlR):
+    def forward(self, slab, P, lvlP, lvlQ, lvlR, out=None):
         """BasicTransform.java:509-566 with its level shift (F5): axis k gets lvlQ, axis j gets
         lvlP, then axis i gets lvlR."""
         self._check(slab, P)
@@ -81,9 +88,9 @@ class SlabVolumeTransform:
         t = self.axis_fn(self.kind, FORWARD, t, p, Q, R, lvlP)          # columns of every slice
         y = self._to_j_slabs(t)
         y = self.axis_fn(self.kind, FORWARD, y, 1, P, y.shape[1] * R, lvlR)
-        return self._to_i_slabs(y)
+        return self._to_i_slabs(y, out)
 
-    def reverse(self, slab, P, lvlP, lvlQ, lvlR):
+    def reverse(self, slab, P, lvlP, lvlQ, lvlR, out=None):
         """BasicTransform.java:602-659: 2-D reverse of every slice (columns, then rows), then axis i."""
         self._check(slab, P)
         p, Q, R = slab.shape
@@ -91,7 +98,7 @@ class SlabVolumeTransform:
         t = self.axis_fn(self.kind, REVERSE, t, p * Q, R, 1, lvlQ)
         y = self._to_j_slabs(t)
         y = self.axis_fn(self.kind, REVERSE, y, 1, P, y.shape[1] * R, lvlR)
-        return self._to_i_slabs(y)
+        return self._to_i_slabs(y, out)
 
     def exchange_bytes(self, slab):
         """Bytes this rank sends per all-to-all (the NVLink term of the roofline)."""
