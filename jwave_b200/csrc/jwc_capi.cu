@@ -106,6 +106,7 @@ extern "C" int jwc_create(jwc_ctx** out, int device) {
     get("str_rev_m", &ctx->str_rev_m);
     get("str_cap", &ctx->str_cap);
     get("str_threads", &ctx->str_threads);
+    get("str_rev_threads", &ctx->str_rev_threads);
     get("str_tma", &ctx->str_tma);
     get("wpt_threads", &ctx->wpt_threads);
   }

@@ -371,7 +371,7 @@ static cudaError_t launch_rev_L(jwc_ctx* ctx, const Taps& taps, FwtRevStrArgs a,
     if (e != cudaSuccess) return e;
   }
   prof_begin(ctx, resident ? "k_fwt_rev_str:resident" : "k_fwt_rev_str:tile", double(a.outer) * a.h0 * a.inner, a.m);
-  kern<<<int(grid), ctx->str_threads, smem, ctx->stream>>>(taps, a);
+  kern<<<int(grid), ctx->str_rev_threads, smem, ctx->stream>>>(taps, a);
   prof_end(ctx);
   ctx->launches++;
   return cudaGetLastError();
