@@ -111,6 +111,13 @@ int jwc_fwt3d(jwc_ctx* ctx, int wid, int dir, const double* in, double* out, int
 int jwc_wpt3d(jwc_ctx* ctx, int wid, int dir, const double* in, double* out, int P, int Q, int R,
               int lvlP, int lvlQ, int lvlR);
 
+/* AncientEgyptianDecomposition.forward/reverse(double[]) around a FastWaveletTransform
+ * (kind = JWC_FWT) or WaveletPacketTransform (kind = JWC_WPT): `batch` signals of ANY length n >= 1.
+ * n is split into its binary expansion, largest block first (MathToolKit.decompose,
+ * tools/MathToolKit.java:57-84), and every 2^p block is transformed at full depth
+ * (transforms/AncientEgyptianDecomposition.java:97-129, :144-183). */
+int jwc_aed1d(jwc_ctx* ctx, int wid, int kind, int dir, const double* in, double* out, int64_t batch, int n);
+
 /* ---- device-resident entry points: `in`/`out` are device pointers on the context's GPU,
  *      must not overlap, and the work is enqueued on the context's stream (no sync) ---------- */
 
@@ -126,6 +133,8 @@ int jwc_fwt3d_dev(jwc_ctx* ctx, int wid, int dir, const double* in, double* out,
                   int lvlP, int lvlQ, int lvlR);
 int jwc_wpt3d_dev(jwc_ctx* ctx, int wid, int dir, const double* in, double* out, int P, int Q, int R,
                   int lvlP, int lvlQ, int lvlR);
+int jwc_aed1d_dev(jwc_ctx* ctx, int wid, int kind, int dir, const double* in, double* out, int64_t batch,
+                  int n);
 /* The building block the 2-D/3-D drivers and the slab-decomposed multi-GPU volume are made of:
  * a dense [outer][n][inner] array, 1-D transform (kind = JWC_FWT | JWC_WPT) along the middle
  * axis of every (outer, inner) line. */

@@ -3,12 +3,12 @@
 The product is libjwave_cuda.so (csrc/, C ABI in include/jwave_cuda.h).  This package is the
 host-side mirror of the reference's plug-in interface on top of it; see transforms.py."""
 from .exceptions import JWaveError, JWaveException, JWaveFailure
-from .transforms import (BasicTransform, CudaContext, CudaFastWaveletTransform,
+from .transforms import (AncientEgyptianDecomposition, BasicTransform, CudaContext, CudaFastWaveletTransform,
                          CudaWaveletPacketTransform, MathToolKit, Transform, WaveletTransform)
 from .wavelets import WAVELET_CLASSES, Wavelet, WaveletBuilder
 
 __all__ = [
-    "BasicTransform", "CudaContext", "CudaFastWaveletTransform", "CudaWaveletPacketTransform",
+    "AncientEgyptianDecomposition", "BasicTransform", "CudaContext", "CudaFastWaveletTransform", "CudaWaveletPacketTransform",
     "JWaveError", "JWaveException", "JWaveFailure", "MathToolKit", "Transform", "WaveletTransform",
     "WAVELET_CLASSES", "Wavelet", "WaveletBuilder",
 ]

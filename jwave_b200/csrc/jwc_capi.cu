@@ -401,6 +401,42 @@ extern "C" int jwc_wpt3d_dev(jwc_ctx* ctx, int wid, int dir, const double* in, d
   return t3d_dev(ctx, wid, JWC_WPT, dir, in, out, P, Q, R, lvlP, lvlQ, lvlR);
 }
 
+// AncientEgyptianDecomposition.java:97-129 / :144-183.  Every 2^p block of the binary expansion of n
+// (MathToolKit.java:57-84, largest first) is gathered from all signals into a dense [batch][2^p]
+// scratch array, transformed at full depth and scattered back (2-D device copies; the blocks of a
+// signal are neither aligned nor equally strided, which the fused kernels want).
+static int aed_dev(jwc_ctx* ctx, int wid, int kind, int dir, const double* in, double* out, int64_t batch, int n) {
+  if (n < 1) return fail(ctx, JWC_ERR_ARG, "the supported number for decomposition is smaller than one");
+  if (batch < 0) return fail(ctx, JWC_ERR_ARG, "negative batch");
+  if (batch == 0) return JWC_OK;
+  if (overlaps(in, out, batch * n)) return fail(ctx, JWC_ERR_ARG, "in and out overlap");
+  JWC_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int top = exponent(n);  // largest block
+  int st = ensure(ctx, ctx->scratch[2], size_t(2) * batch * (size_t(1) << top) * sizeof(double));
+  if (st) return st;
+  double* dense_in = static_cast<double*>(ctx->scratch[2].ptr);
+  double* dense_out = dense_in + batch * (int64_t(1) << top);
+  const size_t pitch = size_t(n) * sizeof(double);
+  int64_t off = 0;
+  for (int p = top; p >= 0; --p) {
+    if (!((n >> p) & 1)) continue;
+    const int len = 1 << p;
+    const size_t row = size_t(len) * sizeof(double);
+    JWC_CUDA(ctx, cudaMemcpy2DAsync(dense_in, row, in + off, pitch, row, size_t(batch), cudaMemcpyDeviceToDevice, ctx->stream));
+    if ((st = axis_dev(ctx, wid, kind, dir, dense_in, dense_out, batch, len, 1, p))) return st;
+    JWC_CUDA(ctx, cudaMemcpy2DAsync(out + off, pitch, dense_out, row, row, size_t(batch), cudaMemcpyDeviceToDevice, ctx->stream));
+    off += len;
+  }
+  return JWC_OK;
+}
+
+extern "C" int jwc_aed1d_dev(jwc_ctx* ctx, int wid, int kind, int dir, const double* in, double* out,
+                             int64_t batch, int n) {
+  int st = check_common(ctx, wid, kind, dir, in, out);
+  if (st) return st;
+  return aed_dev(ctx, wid, kind, dir, in, out, batch, n);
+}
+
 // ---- host-buffer entry points ---------------------------------------------------------------------
 //
 // The batch is cut into chunks of whole items (signals / matrices); chunk c uses staging slot
@@ -485,6 +521,17 @@ extern "C" int jwc_fwt1d(jwc_ctx* ctx, int wid, int dir, const double* in, doubl
 extern "C" int jwc_wpt1d(jwc_ctx* ctx, int wid, int dir, const double* in, double* out, int64_t batch,
                          int n, int level) {
   return t1d_host(ctx, wid, JWC_WPT, dir, in, out, batch, n, level);
+}
+
+extern "C" int jwc_aed1d(jwc_ctx* ctx, int wid, int kind, int dir, const double* in, double* out, int64_t batch,
+                         int n) {
+  int st = check_common(ctx, wid, kind, dir, in, out);
+  if (st) return st;
+  if (n < 1) return fail(ctx, JWC_ERR_ARG, "the supported number for decomposition is smaller than one");
+  if (batch < 0) return fail(ctx, JWC_ERR_ARG, "negative batch");
+  return staged(ctx, in, out, batch, n, [&](const double* di, double* dout, int64_t cnt) {
+    return aed_dev(ctx, wid, kind, dir, di, dout, cnt, n);
+  });
 }
 
 static int t2d_host(jwc_ctx* ctx, int wid, int kind, int dir, const double* in, double* out,

@@ -403,6 +403,58 @@ class CudaWaveletPacketTransform(_CudaWaveletTransform):
         self._name = "Wavelet Packet Transform"  # WaveletPacketTransform.java:53
 
 
+class AncientEgyptianDecomposition(BasicTransform):
+    """Drop-in for jwave/transforms/AncientEgyptianDecomposition.java:38-185: accepts arrays of ANY
+    length by splitting them into their binary expansion (13 = 8 + 4 + 1, MathToolKit.decompose,
+    tools/MathToolKit.java:57-84) and running the wrapped transform at full depth on every block.
+    Here the wrapped transform must be one of the CUDA transforms; all blocks of all signals run on
+    the GPU in one native call (jwc_aed1d)."""
+
+    def __init__(self, waveTransform):
+        super().__init__()
+        if not isinstance(waveTransform, _CudaWaveletTransform):
+            raise JWaveFailure("AncientEgyptianDecomposition - expected a CudaFastWaveletTransform or "
+                               "CudaWaveletPacketTransform")
+        self._basicTransform = waveTransform
+        self._name = "Ancient Egyptian Decomposition"
+
+    def getWavelet(self):
+        return self._basicTransform.getWavelet()
+
+    def _run(self, direction, arr, where):
+        arr = _as_f64(arr)
+        if arr.ndim not in (1, 2) or arr.shape[-1] < 1:
+            raise JWaveFailure("the supported number for decomposition is smaller than one")
+        t = self._basicTransform
+        batch = 1 if arr.ndim == 1 else arr.shape[0]
+        return t._call(lambda h, wid, d, src, dst, b, n: t._ctx._lib.jwc_aed1d(h, wid, t._KIND, d, src, dst, b, n),
+                       where, direction, arr, batch, arr.shape[-1])
+
+    def _forward1(self, arrTime, level=None):
+        if level is not None:  # the reference class has no levelled overload (BasicTransform.java:129 throws)
+            raise JWaveError("BasicTransform#forward - method is not implemented")
+        return self._run(_lib.FORWARD, arrTime, "AncientEgyptianDecomposition#forward")
+
+    def _reverse1(self, arrHilb, level=None):
+        if level is not None:
+            raise JWaveError("BasicTransform#reverse - method is not implemented")
+        return self._run(_lib.REVERSE, arrHilb, "AncientEgyptianDecomposition#reverse")
+
+    def forwardBatch(self, signals):
+        """rows are independent signals of one (arbitrary) length"""
+        return self._run(_lib.FORWARD, signals, "AncientEgyptianDecomposition#forwardBatch")
+
+    def reverseBatch(self, coeffs):
+        return self._run(_lib.REVERSE, coeffs, "AncientEgyptianDecomposition#reverseBatch")
+
+    @staticmethod
+    def decompose(number):
+        """MathToolKit.decompose (tools/MathToolKit.java:57-84): exponents, largest first."""
+        if number < 1:
+            raise JWaveFailure("the supported number for decomposition is smaller than one")
+        return [p for p in range(int(number).bit_length() - 1, -1, -1) if (int(number) >> p) & 1]
+
+
 class Transform:
     """jwave/Transform.java:59-512 - the facade user code holds.  It swallows JWaveException,
     prints it and returns None (Java: null), e.g. Transform.java:81-90."""

@@ -70,6 +70,8 @@ def lib():
         L.jwo_parallel_wpt.argtypes = [C.c_int, _wp, _dp, C.c_long, C.c_int, C.c_int, _dp, C.c_int]
         L.jwo_parallel_2d.argtypes = [C.c_int, C.c_int, _wp, _dp, C.c_long, C.c_int, C.c_int, C.c_int,
                                       C.c_int, _dp, C.c_int]
+        L.jwo_decompose.argtypes = [C.c_int, C.POINTER(C.c_int)]
+        L.jwo_aed.argtypes = [C.c_int, C.c_int, _wp, _dp, C.c_int, _dp]
         L.jwo_max_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -181,6 +183,22 @@ def parallel_2d(kind, direction, name, x, lvlM, lvlN, threads=0):
     b, rows, cols = x.shape
     _check(lib().jwo_parallel_2d(kind, direction, wavelet(name), _p(x), b, rows, cols, lvlM, lvlN, _p(out), threads))
     return out
+
+
+def decompose(number):
+    buf = (C.c_int * 32)()
+    cnt = lib().jwo_decompose(int(number), buf)
+    return [buf[i] for i in range(cnt)]
+
+
+def aed(kind, direction, name, x):
+    """AncientEgyptianDecomposition over the given 1-D array of ANY length (rows of a 2-D array)."""
+    x = _in(x)
+    flat = x.reshape(-1, x.shape[-1])
+    out = np.empty_like(flat)
+    for i in range(flat.shape[0]):
+        _check(lib().jwo_aed(kind, direction, wavelet(name), _p(flat[i]), flat.shape[1], _p(out[i])))
+    return out.reshape(x.shape)
 
 
 def max_threads():

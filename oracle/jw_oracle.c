@@ -421,6 +421,40 @@ int jwo_3d(int kind, int dir, const jwo_wavelet* w, const double* in, int P, int
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Ancient Egyptian decomposition (arbitrary lengths)
+ * ---------------------------------------------------------------------------------------- */
+
+/* tools/MathToolKit.java:57-84 */
+int jwo_decompose(int number, int* out) {
+  if (number < 1) return 0;
+  int pos = 0;
+  double current = (double)number;
+  while (current >= 1.) {
+    int power = jwo_get_exponent(current);
+    out[pos] = power;
+    current = current - ldexp(1., power); /* MathToolKit.scalb( 1., power ) */
+    pos++;
+  }
+  return pos;
+}
+
+/* transforms/AncientEgyptianDecomposition.java:97-129 (forward) and :144-183 (reverse) */
+int jwo_aed(int kind, int dir, const jwo_wavelet* w, const double* in, int n, double* out) {
+  int mult[32];
+  int cnt = jwo_decompose(n, mult);
+  if (cnt == 0) return JWO_ERR_ARG;
+  int offSet = 0;
+  for (int m = 0; m < cnt; m++) {
+    int len = (int)ldexp(1., mult[m]);
+    /* WaveletTransform.forward(double[]) / reverse(double[]): full depth = log2(len) */
+    int st = jwo_1d(kind, dir, w, in + offSet, len, mult[m], out + offSet);
+    if (st) return st;
+    offSet += len;
+  }
+  return JWO_OK;
+}
+
+/* ------------------------------------------------------------------------------------------
  * CPU-baseline drivers.  A small persistent pthread pool stands in for the JVM's
  * ForkJoinPool / fixed executor (no OpenMP runtime in this image).
  * ---------------------------------------------------------------------------------------- */

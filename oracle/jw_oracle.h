@@ -74,6 +74,13 @@ int jwo_2d(int kind, int dir, const jwo_wavelet* w, const double* in, int rows, 
 int jwo_3d(int kind, int dir, const jwo_wavelet* w, const double* in, int P, int Q, int R,
            int lvlP, int lvlQ, int lvlR, double* out);
 
+/* tools/MathToolKit.java:57-84 (decompose): exponents of the binary expansion of `number`, largest
+ * first, e.g. 13 -> {3, 2, 0}.  Returns the count (0 when number < 1); `out` needs 32 entries. */
+int jwo_decompose(int number, int* out);
+/* transforms/AncientEgyptianDecomposition.java:97-129, :144-183: arbitrary length n, split into
+ * 2^p blocks by jwo_decompose, each block transformed at full depth by the wrapped FWT / WPT. */
+int jwo_aed(int kind, int dir, const jwo_wavelet* w, const double* in, int n, double* out);
+
 /* CPU-baseline drivers (OpenMP).  `threads` <= 0 means all available. Return the status of the
  * first failing signal or JWO_OK. */
 /* independent signals on a fixed pool, pattern of test ParallelizationOpportunityTest.java:79-110 */

@@ -212,6 +212,26 @@ def test_independent_filters_take_the_one_level_kernels():
             close(t.reverse(x, level), ref_r, 10 * np.abs(ref_r).max())
 
 
+@pytest.mark.parametrize("kind", ["fwt", "wpt"])
+def test_ancient_egyptian_decomposition(kind):
+    """AncientEgyptianDecomposition over the CUDA transforms: arbitrary lengths, single signals and
+    batches, against the oracle's restatement (AncientEgyptianDecomposition.java:97-183)."""
+    for cls in ("Haar1", "Daubechies4", "Coiflet5"):
+        aed = jw.AncientEgyptianDecomposition(make(kind, cls))
+        for n in (1, 3, 13, 100, 1000, 4097, 65537):
+            x = rng_signal(n + 1, n)
+            cf = co.aed(okind(kind), co.FORWARD, cls, x)
+            close(aed.forward(x), cf, np.abs(x).max())
+            close(aed.reverse(cf), co.aed(okind(kind), co.REVERSE, cls, cf), np.abs(cf).max())
+        xb = rng_signal(5, 37, 1234)
+        cb = co.aed(okind(kind), co.FORWARD, cls, xb)
+        close(aed.forwardBatch(xb), cb, np.abs(xb).max())
+        close(aed.reverseBatch(cb), co.aed(okind(kind), co.REVERSE, cls, cb), np.abs(cb).max())
+        assert jw.Transform(aed).forward(np.ones(12)) is not None
+        with pytest.raises(jw.JWaveError):
+            aed.forward(np.ones(12), 2)
+
+
 def test_abi_status_codes():
     """Raw C-ABI status codes (include/jwave_cuda.h) without the Python pre-checks."""
     import ctypes as C

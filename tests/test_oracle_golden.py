@@ -139,3 +139,23 @@ def test_2d_3d_drivers_three_ways(kind):
         co.transform_3d(k, co.FORWARD, "Coiflet2", s, 4, 3, 2)
     c = rng_signal(5, 8, 8, 8)
     assert np.array_equal(co.transform_3d(k, co.FORWARD, "Coiflet2", c), t.forward(c))
+
+
+def test_ancient_egyptian_decomposition():
+    """AncientEgyptianDecomposition.java:97-183 + MathToolKit.decompose (:57-84): no vectors in the
+    reference, so the restatement is pinned by composition - the result is the wrapped transform
+    applied at full depth to every 2^p block of the binary expansion, largest block first."""
+    import jwave_b200 as jw
+    assert co.decompose(13) == [3, 2, 0] and co.decompose(1) == [0] and co.decompose(64) == [6]
+    for n in (1, 2, 3, 13, 100, 1000, 4097):
+        assert co.decompose(n) == jw.AncientEgyptianDecomposition.decompose(n)
+        assert sum(1 << p for p in co.decompose(n)) == n
+        x = rng_signal(n, n)
+        for kind in (co.FWT, co.WPT):
+            f = co.aed(kind, co.FORWARD, "Daubechies4", x)
+            off, parts = 0, []
+            for p in co.decompose(n):
+                parts.append(co.transform_1d(kind, co.FORWARD, "Daubechies4", x[off:off + (1 << p)]))
+                off += 1 << p
+            assert np.array_equal(f, np.concatenate(parts))
+            assert np.abs(co.aed(kind, co.REVERSE, "Daubechies4", f) - x).max() < 1e-9
