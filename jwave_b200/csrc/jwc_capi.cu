@@ -92,7 +92,6 @@ extern "C" int jwc_create(jwc_ctx** out, int device) {
     get("rev_tile", &ctx->rev_tile);
     get("rev_m", &ctx->rev_m);
     get("rev_rs", &ctx->rev_rs);
-    get("dbg", &ctx->dbg);
     get("fwd_threads", &ctx->fwd_threads);
     get("rev_threads", &ctx->rev_threads);
     get("res_cap", &ctx->res_cap);

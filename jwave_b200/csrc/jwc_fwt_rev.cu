@@ -94,8 +94,6 @@ k_fwt_rev(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevArgs 
     __syncthreads();
 
     for (int k = m; k >= 1; --k) {
-      if (a.dbg == 2 && k > 1) continue;   // timing experiment: only the last level
-      if (a.dbg == 3) break;               // timing experiment: load only
       const double2* A = smem2 + a.offA[k & 1];
       const double2* D = smem2 + a.offD[k];
       double2* Y = smem2 + a.offA[(k - 1) & 1];
@@ -115,7 +113,7 @@ k_fwt_rev(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevArgs 
         if (k > 1) {
 #pragma unroll
           for (int e = 0; e < kRS; ++e) Y[pad2(kRS * g + e)] = make_double2(t[2 * e], t[2 * e + 1]);
-        } else if (a.dbg != 1 || t[0] == 123.456) {   // dbg 1: timing experiment without the stores
+        } else {
           double* y = a.dst + line * a.dst_os + t0 + 2 * kRS * g;
 #pragma unroll
           for (int e = 0; e < kRS / 2; ++e) st_global_v4(y + 4 * e, t[4 * e], t[4 * e + 1], t[4 * e + 2], t[4 * e + 3]);

@@ -32,7 +32,6 @@ struct FwtRevArgs {
   double* dst; int64_t dst_os;          // a_0 lines (width h0)
   int64_t lines;
   int h0, m, T, G;
-  int dbg;                              // timing experiments only (0 in production)
   // filled in by the launcher
   int tiles_per_line, ru8;
   int F[kMaxFuse + 2], g0[kMaxFuse + 1], len[kMaxFuse + 1], offD[kMaxFuse + 1], offA[2];

@@ -302,7 +302,7 @@ static cudaError_t fwt_reverse(jwc_ctx* ctx, const WaveletRec& w, const double* 
   for (int i = 0; i < npass; ++i) {
     const Pass& p = passes[i];
     const bool last = (p.h0 == n);
-    a.h0 = p.h0; a.m = p.m; a.dbg = ctx->dbg;
+    a.h0 = p.h0; a.m = p.m;
     a.T = (p.resident || p.h0 < ctx->rev_tile) ? p.h0 : ctx->rev_tile;
     a.G = p.resident ? resident_lines(p.h0, 175) : 1;  // rev: (h + h/2 + h/4) samples, padded 1.25
     a.dst = last ? out : S[i & 1];
