@@ -118,6 +118,13 @@ int jwc_wpt3d(jwc_ctx* ctx, int wid, int dir, const double* in, double* out, int
  * (transforms/AncientEgyptianDecomposition.java:97-129, :144-183). */
 int jwc_aed1d(jwc_ctx* ctx, int wid, int kind, int dir, const double* in, double* out, int64_t batch, int n);
 
+/* CompressorMagnitude.compress(double[] / double[][] / double[][][]) - the same operation on `count`
+ * coefficients of any rank (compressions/CompressorMagnitude.java:52-118, compressions/Compressor.java:
+ * 97-110): magnitude = mean |c|, then c -> (|c| >= magnitude * threshold ? c : 0).  *magnitude (may be
+ * NULL) receives the mean.  threshold must be > 0. */
+int jwc_compress_magnitude(jwc_ctx* ctx, const double* in, double* out, int64_t count, double threshold,
+                           double* magnitude);
+
 /* ---- device-resident entry points: `in`/`out` are device pointers on the context's GPU,
  *      must not overlap, and the work is enqueued on the context's stream (no sync) ---------- */
 
@@ -135,6 +142,9 @@ int jwc_wpt3d_dev(jwc_ctx* ctx, int wid, int dir, const double* in, double* out,
                   int lvlP, int lvlQ, int lvlR);
 int jwc_aed1d_dev(jwc_ctx* ctx, int wid, int kind, int dir, const double* in, double* out, int64_t batch,
                   int n);
+/* device variant: *magnitude_dev (device pointer, may be NULL) receives the mean, no host sync */
+int jwc_compress_magnitude_dev(jwc_ctx* ctx, const double* in, double* out, int64_t count, double threshold,
+                               double* magnitude_dev);
 /* The building block the 2-D/3-D drivers and the slab-decomposed multi-GPU volume are made of:
  * a dense [outer][n][inner] array, 1-D transform (kind = JWC_FWT | JWC_WPT) along the middle
  * axis of every (outer, inner) line. */

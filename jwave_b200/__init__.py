@@ -2,13 +2,14 @@
 
 The product is libjwave_cuda.so (csrc/, C ABI in include/jwave_cuda.h).  This package is the
 host-side mirror of the reference's plug-in interface on top of it; see transforms.py."""
+from .compressions import Compressor, CompressorMagnitude
 from .exceptions import JWaveError, JWaveException, JWaveFailure
 from .transforms import (AncientEgyptianDecomposition, BasicTransform, CudaContext, CudaFastWaveletTransform,
                          CudaWaveletPacketTransform, MathToolKit, Transform, WaveletTransform)
 from .wavelets import WAVELET_CLASSES, Wavelet, WaveletBuilder
 
 __all__ = [
-    "AncientEgyptianDecomposition", "BasicTransform", "CudaContext", "CudaFastWaveletTransform", "CudaWaveletPacketTransform",
+    "AncientEgyptianDecomposition", "BasicTransform", "Compressor", "CompressorMagnitude", "CudaContext", "CudaFastWaveletTransform", "CudaWaveletPacketTransform",
     "JWaveError", "JWaveException", "JWaveFailure", "MathToolKit", "Transform", "WaveletTransform",
     "WAVELET_CLASSES", "Wavelet", "WaveletBuilder",
 ]

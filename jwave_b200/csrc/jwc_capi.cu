@@ -436,6 +436,64 @@ extern "C" int jwc_aed1d_dev(jwc_ctx* ctx, int wid, int kind, int dir, const dou
   return aed_dev(ctx, wid, kind, dir, in, out, batch, n);
 }
 
+// CompressorMagnitude on device-resident coefficients; the magnitude stays on the device
+static int compress_dev(jwc_ctx* ctx, const double* in, double* out, int64_t count, double threshold,
+                        double* magnitude_dev) {
+  if (!ctx) return JWC_ERR_ARG;
+  if (!in || !out) return fail(ctx, JWC_ERR_ARG, "null data pointer");
+  if (!(threshold > 0.)) return fail(ctx, JWC_ERR_ARG, "Compressor - given threshold should be larger than zero!");
+  if (count < 1) return fail(ctx, JWC_ERR_ARG, "Compressor - empty array");
+  JWC_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int blocks = ctx->sm_count * 8;
+  int st = ensure(ctx, ctx->scratch[3], size_t(blocks + 1) * sizeof(double));
+  if (st) return st;
+  double* scratch = static_cast<double*>(ctx->scratch[3].ptr);
+  cudaError_t e = launch_compress_magnitude(ctx, in, out, count, threshold, scratch, blocks);
+  if (e != cudaSuccess) {
+    ctx->err = std::string("compress: ") + cudaGetErrorString(e);
+    return JWC_ERR_CUDA;
+  }
+  if (magnitude_dev)
+    JWC_CUDA(ctx, cudaMemcpyAsync(magnitude_dev, scratch + blocks, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  return JWC_OK;
+}
+
+extern "C" int jwc_compress_magnitude_dev(jwc_ctx* ctx, const double* in, double* out, int64_t count,
+                                          double threshold, double* magnitude_dev) {
+  return compress_dev(ctx, in, out, count, threshold, magnitude_dev);
+}
+
+// Host buffers: the magnitude is a global mean, so the whole array has to be resident at once.
+extern "C" int jwc_compress_magnitude(jwc_ctx* ctx, const double* in, double* out, int64_t count, double threshold,
+                                      double* magnitude) {
+  if (!ctx) return JWC_ERR_ARG;
+  if (!in || !out) return fail(ctx, JWC_ERR_ARG, "null data pointer");
+  if (!(threshold > 0.)) return fail(ctx, JWC_ERR_ARG, "Compressor - given threshold should be larger than zero!");
+  if (count < 1) return fail(ctx, JWC_ERR_ARG, "Compressor - empty array");
+  JWC_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t bytes = size_t(count) * sizeof(double);
+  int st;
+  if ((st = ensure(ctx, ctx->stage_in[0], bytes)) || (st = ensure(ctx, ctx->stage_out[0], bytes))) return st;
+  double* d_in = static_cast<double*>(ctx->stage_in[0].ptr);
+  double* d_out = static_cast<double*>(ctx->stage_out[0].ptr);
+  cudaStream_t user_stream = ctx->stream;
+  if (user_stream != ctx->own_stream) JWC_CUDA(ctx, cudaStreamSynchronize(user_stream));
+  ctx->stream = ctx->own_stream;
+  cudaError_t e = cudaMemcpyAsync(d_in, in, bytes, cudaMemcpyHostToDevice, ctx->stream);
+  st = (e == cudaSuccess) ? compress_dev(ctx, d_in, d_out, count, threshold, nullptr) : JWC_ERR_CUDA;
+  if (!st) {
+    e = cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && magnitude)
+      e = cudaMemcpyAsync(magnitude, static_cast<double*>(ctx->scratch[3].ptr) + ctx->sm_count * 8, sizeof(double),
+                          cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) st = JWC_ERR_CUDA;
+  }
+  ctx->stream = user_stream;
+  if (st == JWC_ERR_CUDA && e != cudaSuccess) ctx->err = std::string("compress: ") + cudaGetErrorString(e);
+  return st;
+}
+
 // ---- host-buffer entry points ---------------------------------------------------------------------
 //
 // The batch is cut into chunks of whole items (signals / matrices); chunk c uses staging slot

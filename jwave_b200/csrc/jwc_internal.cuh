@@ -115,4 +115,8 @@ struct RevLevelArgs {
 cudaError_t launch_fwd_level_generic(jwc_ctx* ctx, int L, const Taps& taps, const FwdLevelArgs& a);
 cudaError_t launch_rev_level_generic(jwc_ctx* ctx, int L, const Taps& taps, const RevLevelArgs& a);
 
+// jwc_compress.cu: CompressorMagnitude; `scratch` holds blocks + 1 doubles (partials, magnitude)
+cudaError_t launch_compress_magnitude(jwc_ctx* ctx, const double* in, double* out, int64_t n, double threshold,
+                                      double* scratch, int blocks);
+
 }  // namespace jwc

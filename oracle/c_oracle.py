@@ -72,6 +72,8 @@ def lib():
                                       C.c_int, _dp, C.c_int]
         L.jwo_decompose.argtypes = [C.c_int, C.POINTER(C.c_int)]
         L.jwo_aed.argtypes = [C.c_int, C.c_int, _wp, _dp, C.c_int, _dp]
+        L.jwo_compress_magnitude.restype = C.c_double
+        L.jwo_compress_magnitude.argtypes = [_dp, C.c_long, C.c_double, _dp]
         L.jwo_max_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -199,6 +201,14 @@ def aed(kind, direction, name, x):
     for i in range(flat.shape[0]):
         _check(lib().jwo_aed(kind, direction, wavelet(name), _p(flat[i]), flat.shape[1], _p(out[i])))
     return out.reshape(x.shape)
+
+
+def compress_magnitude(x, threshold):
+    """CompressorMagnitude.compress on an array of any rank -> (compressed, magnitude)."""
+    x = _in(x)
+    out = np.empty_like(x)
+    mag = lib().jwo_compress_magnitude(_p(x.reshape(-1)), x.size, float(threshold), _p(out.reshape(-1)))
+    return out, mag
 
 
 def max_threads():

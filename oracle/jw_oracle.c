@@ -454,6 +454,20 @@ int jwo_aed(int kind, int dir, const jwo_wavelet* w, const double* in, int n, do
   return JWO_OK;
 }
 
+/* compressions/CompressorMagnitude.java:52-68 and compressions/Compressor.java:97-110 */
+double jwo_compress_magnitude(const double* arr, long n, double threshold, double* out) {
+  double magnitude = 0.;
+  for (long i = 0; i < n; i++) magnitude += fabs(arr[i]);
+  magnitude /= (double)n;
+  for (long i = 0; i < n; i++) {
+    if (fabs(arr[i]) >= magnitude * threshold)
+      out[i] = arr[i];
+    else
+      out[i] = 0.;
+  }
+  return magnitude;
+}
+
 /* ------------------------------------------------------------------------------------------
  * CPU-baseline drivers.  A small persistent pthread pool stands in for the JVM's
  * ForkJoinPool / fixed executor (no OpenMP runtime in this image).

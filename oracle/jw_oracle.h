@@ -81,6 +81,11 @@ int jwo_decompose(int number, int* out);
  * 2^p blocks by jwo_decompose, each block transformed at full depth by the wrapped FWT / WPT. */
 int jwo_aed(int kind, int dir, const jwo_wavelet* w, const double* in, int n, double* out);
 
+/* compressions/CompressorMagnitude.java:52-68 over compressions/Compressor.java:97-110: magnitude =
+ * mean |x| (left-to-right sum), out[i] = |x[i]| >= magnitude * threshold ? x[i] : 0.  Returns the
+ * magnitude. */
+double jwo_compress_magnitude(const double* arr, long n, double threshold, double* out);
+
 /* CPU-baseline drivers (OpenMP).  `threads` <= 0 means all available. Return the status of the
  * first failing signal or JWO_OK. */
 /* independent signals on a fixed pool, pattern of test ParallelizationOpportunityTest.java:79-110 */

@@ -232,6 +232,25 @@ def test_ancient_egyptian_decomposition(kind):
             aed.forward(np.ones(12), 2)
 
 
+def test_compressor_magnitude():
+    """CompressorMagnitude (compressions/CompressorMagnitude.java:52-118) on 1-D / 2-D / 3-D coefficient
+    arrays against the oracle: same magnitude to rounding, same zero pattern (coefficients sitting
+    exactly on the cut are excluded from the comparison - the GPU sums |c| in a different order)."""
+    t = make("fwt", "Daubechies4")
+    for shape, thr in (((4096,), 1.0), ((256, 512), 0.5), ((16, 32, 64), 2.0), ((1 << 20,), 1.3)):
+        x = rng_signal(sum(shape), *shape)
+        c = t.forward(x) if len(shape) == 1 else x  # compress real coefficients in the 1-D cases
+        ref, mag = co.compress_magnitude(c, thr)
+        comp = jw.CompressorMagnitude(thr)
+        got = comp.compress(c)
+        assert abs(comp.getMagnitude() - mag) <= 1e-13 * mag
+        safe = np.abs(np.abs(c) - mag * thr) > 1e-12 * mag  # not within rounding of the cut
+        assert np.array_equal(got[safe], ref[safe])
+        assert got.shape == c.shape
+        assert abs(comp.calcCompressionRate(got) - comp.calcCompressionRate(ref)) < 1e-3
+    assert jw.CompressorMagnitude(-3.0).getThreshold() == 1.0  # Compressor.java:52-66
+
+
 def test_abi_status_codes():
     """Raw C-ABI status codes (include/jwave_cuda.h) without the Python pre-checks."""
     import ctypes as C

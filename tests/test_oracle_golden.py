@@ -159,3 +159,14 @@ def test_ancient_egyptian_decomposition():
                 off += 1 << p
             assert np.array_equal(f, np.concatenate(parts))
             assert np.abs(co.aed(kind, co.REVERSE, "Daubechies4", f) - x).max() < 1e-9
+
+
+def test_compressor_magnitude_restatement():
+    """compressions/CompressorMagnitude.java:52-68 + Compressor.java:97-110 (no vectors in the
+    reference): magnitude is the mean |c|; coefficients below magnitude * threshold become zero."""
+    x = np.array([1.0, -2.0, 3.0, -4.0, 0.5, -0.25, 6.0, 0.0])
+    out, mag = co.compress_magnitude(x, 1.0)
+    assert mag == np.abs(x).sum() / 8
+    assert np.array_equal(out, np.where(np.abs(x) >= mag, x, 0.0))
+    out2, _ = co.compress_magnitude(x, 0.1)
+    assert np.array_equal(out2, np.where(np.abs(x) >= 0.1 * mag, x, 0.0))
