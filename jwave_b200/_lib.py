@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libjwave_cuda.so")
+# JWAVE_CUDA_LIB points at another build of the same library (A/B runs of kernel variants)
+SO_PATH = os.environ.get("JWAVE_CUDA_LIB") or os.path.join(_HERE, "libjwave_cuda.so")
 
 OK, ERR_NOT_BINARY, ERR_LEVEL, ERR_ARG, ERR_CUDA, ERR_NCCL = range(6)
 FORWARD, REVERSE = 0, 1

@@ -20,6 +20,37 @@
 
 namespace jwc {
 
+// Shared-memory layout of the reverse kernels.  A thread reads windows of consecutive double2 and
+// neighbouring threads start kRS/2 = 2 double2 apart at ANY alignment, so the 8 lanes of an LDS.128
+// phase cover one 16-slot window at stride 2: with double2 k stored at k ^ bit3(k) the slots of the
+// upper half of every 16-block trade parity and the 8 lanes land on 8 distinct 16-byte bank groups -
+// without pad slots (the stride-4 padding of the forward kernels, pad2, gives 2-way conflicts here).
+__device__ __forceinline__ int lay(int k2) { return k2 ^ ((k2 >> 3) & 1); }
+__host__ __device__ constexpr int lay_size(int n2) { return (n2 + 1) & ~1; }
+__device__ __forceinline__ double lay_scalar(const double2* buf, int i) {
+  return reinterpret_cast<const double*>(buf)[2 * lay(i >> 1) + (i & 1)];
+}
+
+// Store the kRS double2 a group produced at slots kRS g .. kRS g + kRS - 1.  For kRS = 4 the lanes of an
+// STS.128 phase are 4 slots apart (32 slots in all): lanes 4-7 store their pairs in the order 2, 3, 0, 1,
+// which together with the bit-3 swap makes every phase conflict-free.
+template <int kRS>
+__device__ __forceinline__ void store_group(double2* Y, int g, const double (&t)[2 * kRS]) {
+  if constexpr (kRS == 4) {
+    const bool rot = (g >> 2) & 1;
+    const int base = 4 * g, x = (g >> 1) & 1, r2 = rot ? 2 : 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const double v0 = rot ? t[2 * (e ^ 2)] : t[2 * e];
+      const double v1 = rot ? t[2 * (e ^ 2) + 1] : t[2 * e + 1];
+      Y[(base + (e ^ r2)) ^ x] = make_double2(v0, v1);
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < kRS; ++e) Y[lay(kRS * g + e)] = make_double2(t[2 * e], t[2 * e + 1]);
+  }
+}
+
 // RS consecutive slots p = RS g' .. RS g' + RS - 1 (RS = 8 or 4) -> t[2 RS]:
 //   t[2pp + r] = sum_q a[p - q] lo[2q + r] + d[p - q] hi[2q + r].
 // `a2(w)` / `d2(w)` return double2 number (RS/2 g' + RS/2 - 1 - w) of the a / d arrays, w = 0 .. L/4 + RS/2 - 1.
@@ -75,25 +106,28 @@ k_fwt_rev(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevArgs 
     const int T = a.T;
     const int t0 = tile * T;
     const double* lineD = a.srcD + line * a.srcD_os;
-    // stage d_k (k = 1..m) and a_m; local sample j of level k is absolute slot O_k + j (periodic)
-    for (int k = 1; k <= m; ++k) {
+    // stage d_k (k = 1..m) and a_m, coarsest level first and one cp.async group per level: level k
+    // starts as soon as ITS coefficients have landed, while d_1 (half of all bytes) is still in flight.
+    // Local sample j of level k is absolute slot O_k + j (periodic).
+    for (int k = m; k >= 1; --k) {
       const int wk = h0 >> k;  // width of a_k and d_k
       const int O = (k == m) ? ((t0 >> k) - a.F[k] - a.ru8) : 2 * ((t0 >> (k + 1)) - a.F[k + 1]);
       double2* D = smem2 + a.offD[k];
       const double* dk = lineD + wk;
       for (int j2 = tid; j2 < a.len[k] / 2; j2 += nthr)
-        cp_async16(&D[pad2(j2)], dk + ((O + 2 * j2) & (wk - 1)));
+        cp_async16(&D[lay(j2)], dk + ((O + 2 * j2) & (wk - 1)));
       if (k == m) {
         double2* A = smem2 + a.offA[m & 1];
         const double* am = a.srcA + line * a.srcA_os;
         for (int j2 = tid; j2 < a.len[k] / 2; j2 += nthr)
-          cp_async16(&A[pad2(j2)], am + ((O + 2 * j2) & (wk - 1)));
+          cp_async16(&A[lay(j2)], am + ((O + 2 * j2) & (wk - 1)));
       }
+      cp_async_commit();
     }
-    cp_async_wait_all();
-    __syncthreads();
 
     for (int k = m; k >= 1; --k) {
+      cp_async_wait_pending(k - 1);  // groups of levels k-1 .. 1 may still be in flight
+      __syncthreads();               // level k staged for every thread, a_k complete
       const double2* A = smem2 + a.offA[k & 1];
       const double2* D = smem2 + a.offD[k];
       double2* Y = smem2 + a.offA[(k - 1) & 1];
@@ -101,18 +135,10 @@ k_fwt_rev(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevArgs 
       const int g0 = a.g0[k];
       for (int g = tid; g < groups; g += nthr) {
         double t[2 * kRS];
-        if constexpr (kRS == 8) {
-          // pad2(4g' + 3 - w) = 5g' + (3 - w) + floor((3 - w) / 4): a compile-time offset per w
-          const int base = 5 * (g + g0);
-          rev_step<L, 8>(taps, [&](int w) { return A[base + (3 - w) + ((3 - w) >> 2)]; },
-                         [&](int w) { return D[base + (3 - w) + ((3 - w) >> 2)]; }, t);
-        } else {
-          const int c = 4 * g0 + (kRS / 2) * g + kRS / 2 - 1;
-          rev_step<L, kRS>(taps, [&](int w) { return A[pad2(c - w)]; }, [&](int w) { return D[pad2(c - w)]; }, t);
-        }
+        const int c = 4 * g0 + (kRS / 2) * g + kRS / 2 - 1;
+        rev_step<L, kRS>(taps, [&](int w) { return A[lay(c - w)]; }, [&](int w) { return D[lay(c - w)]; }, t);
         if (k > 1) {
-#pragma unroll
-          for (int e = 0; e < kRS; ++e) Y[pad2(kRS * g + e)] = make_double2(t[2 * e], t[2 * e + 1]);
+          store_group<kRS>(Y, g, t);
         } else {
           double* y = a.dst + line * a.dst_os + t0 + 2 * kRS * g;
 #pragma unroll
@@ -120,7 +146,6 @@ k_fwt_rev(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevArgs 
           static_assert(kRS >= 2, "a group stores at least 4 samples");
         }
       }
-      __syncthreads();
     }
   } else {
     // ---------------- resident mode ----------------
@@ -135,7 +160,7 @@ k_fwt_rev(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevArgs 
       const int per_line = h0 >> 1;
       for (int it = tid; it < nlines * per_line; it += nthr) {
         const int ln = it / per_line, k2 = it - ln * per_line;
-        cp_async16(&C[ln * capC + pad2(k2)], a.srcD + (line0 + ln) * a.srcD_os + 2 * k2);
+        cp_async16(&C[ln * capC + lay(k2)], a.srcD + (line0 + ln) * a.srcD_os + 2 * k2);
       }
       cp_async_wait_all();
       __syncthreads();
@@ -154,12 +179,10 @@ k_fwt_rev(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevArgs 
           const double2* al = from_c ? cl : P[k & 1] + ln * capP[k & 1];
           const int c = (kRS / 2) * g + kRS / 2 - 1;
           double t[2 * kRS];
-          rev_step<L, kRS>(taps, [&](int w) { return al[pad2((c - w) & mask2)]; },
-                       [&](int w) { return cl[pad2(doff + ((c - w) & mask2))]; }, t);
+          rev_step<L, kRS>(taps, [&](int w) { return al[lay((c - w) & mask2)]; },
+                       [&](int w) { return cl[lay(doff + ((c - w) & mask2))]; }, t);
           if (!last) {
-            double2* y = P[(k - 1) & 1] + ln * capP[(k - 1) & 1];
-#pragma unroll
-            for (int e = 0; e < kRS; ++e) y[pad2(kRS * g + e)] = make_double2(t[2 * e], t[2 * e + 1]);
+            store_group<kRS>(P[(k - 1) & 1] + ln * capP[(k - 1) & 1], g, t);
           } else {
             double* y = a.dst + (line0 + ln) * a.dst_os + 2 * kRS * g;
 #pragma unroll
@@ -178,14 +201,14 @@ k_fwt_rev(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevArgs 
 #pragma unroll
           for (int q = 0; q < L / 2; ++q) {
             const int i = (p - q) & mask;
-            const double av = sm_scalar(al, i), dv = sm_scalar(cl, half + i);
+            const double av = lay_scalar(al, i), dv = lay_scalar(cl, half + i);
             t0v = fma(av, taps.lo[2 * q], t0v);
             t0v = fma(dv, hi_tap<L>(taps, 2 * q), t0v);
             t1v = fma(av, taps.lo[2 * q + 1], t1v);
             t1v = fma(dv, hi_tap<L>(taps, 2 * q + 1), t1v);
           }
           if (!last) {
-            P[(k - 1) & 1][ln * capP[(k - 1) & 1] + pad2(p)] = make_double2(t0v, t1v);
+            P[(k - 1) & 1][ln * capP[(k - 1) & 1] + lay(p)] = make_double2(t0v, t1v);
           } else {
             double* y = a.dst + (line0 + ln) * a.dst_os + 2 * p;
             y[0] = t0v;
@@ -221,8 +244,8 @@ static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, FwtRevArgs a, bool r
       a.len[k] = (k == a.m) ? (a.T >> k) + a.F[k] + a.ru8 : (a.T >> k) + 2 * a.F[k + 1];
       a.g0[k] = (k == a.m) ? a.ru8 / 8 : (2 * a.F[k + 1] - a.F[k]) / 8;
       a.offD[k] = off;
-      off += pad2_size(a.len[k] / 2);
-      if (pad2_size(a.len[k] / 2) > capA[k & 1]) capA[k & 1] = pad2_size(a.len[k] / 2);
+      off += lay_size(a.len[k] / 2);
+      if (lay_size(a.len[k] / 2) > capA[k & 1]) capA[k & 1] = lay_size(a.len[k] / 2);
     }
     a.offA[0] = off;
     a.offA[1] = off + capA[0];
@@ -232,9 +255,10 @@ static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, FwtRevArgs a, bool r
     if (ctas > 0x7fffffff) return cudaErrorInvalidConfiguration;
     grid = int(ctas);
   } else {
-    a.capC = pad2_size(a.h0 / 2);
-    a.capP[1] = pad2_size(max(1, a.h0 / 4));  // a_1 (odd levels): h0 / 2 samples
-    a.capP[0] = pad2_size(max(1, a.h0 / 8));  // a_2 (even levels): h0 / 4 samples
+    // + 1: successive lines start on the other slot parity (short lines share an LDS phase)
+    a.capC = lay_size(a.h0 / 2) + 1;
+    a.capP[1] = lay_size(max(1, a.h0 / 4)) + 1;  // a_1 (odd levels): h0 / 2 samples
+    a.capP[0] = lay_size(max(1, a.h0 / 8)) + 1;  // a_2 (even levels): h0 / 4 samples
     smem = size_t(a.G) * (a.capC + a.capP[0] + a.capP[1]) * sizeof(double2);
     grid = int((a.lines + a.G - 1) / a.G);
   }

@@ -304,7 +304,7 @@ static cudaError_t fwt_reverse(jwc_ctx* ctx, const WaveletRec& w, const double* 
     const bool last = (p.h0 == n);
     a.h0 = p.h0; a.m = p.m;
     a.T = (p.resident || p.h0 < ctx->rev_tile) ? p.h0 : ctx->rev_tile;
-    a.G = p.resident ? resident_lines(p.h0, 175) : 1;  // rev: (h + h/2 + h/4) samples, padded 1.25
+    a.G = p.resident ? resident_lines(p.h0, 140) : 1;  // rev: (h + h/2 + h/4) samples, unpadded
     a.dst = last ? out : S[i & 1];
     a.dst_os = last ? n : p.h0;
     JWC_TRY(launch_fwt_rev(ctx, w.L, w.re, a, p.resident));
