@@ -70,7 +70,9 @@ struct WptFwdArgs {
   double* dst; int64_t dst_os;          // output lines: 2^m leaf packets of width h >> m, natural order
   int64_t lines;
   int h, m, T, G;
-  int tiles_per_line, buf_cap;          // filled in by the launcher
+  // filled in by the launcher
+  int tiles_per_line, lg_tpl, lg_T, buf_cap;
+  int cap[kMaxFuse + 1];                // tile mode: per-node capacity (double2) of level k
 };
 int wpt_tile_levels(int L, int T, int want, size_t smem_limit, int R);
 cudaError_t launch_wpt_fwd(jwc_ctx* ctx, int L, const Taps& taps, const WptFwdArgs& a, bool resident);
@@ -82,7 +84,7 @@ struct WptRevArgs {
   int64_t lines;
   int h0, m, T, G;
   // filled in by the launcher
-  int tiles_per_line, ru8, buf_cap;
+  int tiles_per_line, lg_tpl, lg_T, ru8, buf_cap;
   int F[kMaxFuse + 2], g0[kMaxFuse + 1], len[kMaxFuse + 1], cap[kMaxFuse + 1];
 };
 int wpt_rev_tile_levels(int L, int T, int want, size_t smem_limit);

@@ -36,66 +36,103 @@ template <int R> __device__ __forceinline__ void lscalar_store(double2* buf, int
   reinterpret_cast<double*>(buf)[2 * padr<R>(i >> 1) + (i & 1)] = v;
 }
 
-template <int L, bool RESIDENT, int R>
+// ---- tile mode ------------------------------------------------------------------------------------
+// CTA = blockDim.x - 32 "main" threads + one tail warp.  At every level the T/2 outputs (per filter) the
+// tile keeps are exactly T / (2R) groups of R, a power of two, so the main warps are always full and
+// the (node, group) split of an item is a shift and a mask.  The halo outputs a node owes the levels
+// below ((2^(m-k) - 1)(L - 2) per node, none at the last level) go to the tail warp, two per step: it
+// runs beside the main warps instead of costing every level one more nearly empty R-wide step.
+template <int L, int R>
 __global__ void __launch_bounds__(512)
-k_wpt_fwd(const __grid_constant__ Taps taps, const WptFwdArgs a) {
+k_wpt_fwd_tile(const __grid_constant__ Taps taps, const __grid_constant__ WptFwdArgs a) {
   extern __shared__ double2 smem2[];
-  const int tid = threadIdx.x, nthr = blockDim.x;
-  const int m = a.m, h = a.h;
-
-  if constexpr (!RESIDENT) {
-    // ---------------- tile mode ----------------
-    const int64_t line = blockIdx.x / a.tiles_per_line;
-    const int tile = int(blockIdx.x % a.tiles_per_line);
-    const int T = a.T;
-    const int n0 = T + ((1 << m) - 1) * (L - 2);
-    double2* cur = smem2;
-    double2* nxt = smem2 + a.buf_cap;
-    const double* src = a.src + line * a.src_os;
-    const int base = tile * T;
-    for (int k2 = tid; k2 < n0 / 2; k2 += nthr)
-      cp_async16(&cur[padr<R>(k2)], src + ((base + 2 * k2) & (h - 1)));
+  constexpr int lgR = (R == 8) ? 3 : 2;
+  static_assert(R == 8 || R == 4, "R is 4 or 8");
+  const int tid = threadIdx.x, nthr = blockDim.x, nmain = nthr - 32;
+  const int m = a.m, h = a.h, T = a.T;
+  const int64_t line = blockIdx.x >> a.lg_tpl;
+  const int tile = int(blockIdx.x) & (a.tiles_per_line - 1);
+  const int base = tile * T;
+  double2* cur = smem2;
+  double2* nxt = smem2 + a.buf_cap;
+  {
+    // stage the tile and its right halo; only the last tile of a line wraps (once: halo <= T / 4 < h).
+    // nthr is a multiple of R, so a step of nthr double2 is a constant step through the padded layout.
+    const int n2 = (T + ((1 << m) - 1) * (L - 2)) >> 1;
+    const int fit2 = min(n2, (h - base) >> 1);
+    const int step = nthr + nthr / R;
+    const double* sp = a.src + line * a.src_os + base + 2 * tid;
+    double2* dp = cur + padr<R>(tid);
+    int k2 = tid;
+    for (; k2 < fit2; k2 += nthr, sp += 2 * nthr, dp += step) cp_async16(dp, sp);
+    sp -= h;
+#pragma unroll 1
+    for (; k2 < n2; k2 += nthr, sp += 2 * nthr, dp += step) cp_async16(dp, sp);
     cp_async_wait_all();
     __syncthreads();
+  }
 
-    double* outl = a.dst + line * a.dst_os;
-    int cap_in = 0;  // per-node capacity of the level being read (one node at level 0)
-    for (int k = 1; k <= m; ++k) {
-      const int n_keep = T >> k;                                    // outputs of each node this tile owns
-      const int n_out = n_keep + ((1 << (m - k)) - 1) * (L - 2);    // incl. halo for the levels below
-      const int groups = (n_out + R - 1) / R;
-      const int cap_out = padr_size<R>(n_out / 2 + R);
-      const int items = groups << (k - 1);                          // nodes_in * groups
-      const bool last = (k == m);
-      // (node, g) walk without a division: it = node * groups + g advances by nthr per step
-      for (int it = tid, node = tid / groups, g = tid - node * groups; it < items; it += nthr, g += nthr) {
-        while (g >= groups) { g -= groups; ++node; }
-        const double2* w = cur + node * cap_in + (R + 1) * g;        // padr(R g + q) == (R + 1) g + q + q / R
+  int cap_in = 0;  // per-node capacity of the level being read (one node at level 0)
+  for (int k = 1; k <= m; ++k) {
+    const int cap_out = a.cap[k];
+    const bool last = (k == m);
+    if (tid < nmain) {
+      const int lg_gpn = a.lg_T - k - lgR;  // groups per node = (T >> k) / R
+      for (int it = tid; it < ((T >> 1) >> lgR); it += nmain) {
+        const int node = it >> lg_gpn, g = it & ((1 << lg_gpn) - 1);
+        const double2* w = cur + node * cap_in + (R + 1) * g;  // padr(R g + q) == (R + 1) g + q + q / R
         double lo[R], hi[R];
         fwd_stepR<L, R>(taps, [&](int q) { return w[q + q / R]; }, lo, hi);
         if (!last) {
-          double2* na = nxt + (2 * node) * cap_out;
+          // padr(R/2 g + e) == R/2 g + (g >> 1) + e for e < R/2
+          double2* na = nxt + (2 * node) * cap_out + (R / 2) * g + (g >> 1);
           double2* nd = na + cap_out;
 #pragma unroll
           for (int e = 0; e < R / 2; ++e) {
-            na[padr<R>(R / 2 * g + e)] = make_double2(lo[2 * e], lo[2 * e + 1]);
-            nd[padr<R>(R / 2 * g + e)] = make_double2(hi[2 * e], hi[2 * e + 1]);
+            na[e] = make_double2(lo[2 * e], lo[2 * e + 1]);
+            nd[e] = make_double2(hi[2 * e], hi[2 * e + 1]);
           }
-        } else if (R * g < n_keep) {
-          double* pa = outl + int64_t(2 * node) * (h >> m) + tile * n_keep + R * g;
+        } else {
+          const int leaf = h >> m;
+          double* pa = a.dst + line * a.dst_os + int64_t(2 * node) * leaf + (base >> m) + R * g;
 #pragma unroll
           for (int e = 0; e < R / 4; ++e) {
             st_global_v4(pa + 4 * e, lo[4 * e], lo[4 * e + 1], lo[4 * e + 2], lo[4 * e + 3]);
-            st_global_v4(pa + (h >> m) + 4 * e, hi[4 * e], hi[4 * e + 1], hi[4 * e + 2], hi[4 * e + 3]);
+            st_global_v4(pa + leaf + 4 * e, hi[4 * e], hi[4 * e + 1], hi[4 * e + 2], hi[4 * e + 3]);
           }
         }
       }
-      __syncthreads();
-      double2* t = cur; cur = nxt; nxt = t;
-      cap_in = cap_out;
+    } else if (!last) {
+      const int n_keep = T >> k;
+      const int per_node = (((1 << (m - k)) - 1) * (L - 2)) >> 1;  // halo steps per node (L - 2 is even)
+      const int items = per_node << (k - 1);
+      int node = 0;
+      for (int it = tid - nmain, j = it; it < items; it += 32, j += 32) {
+        while (j >= per_node) { j -= per_node; ++node; }
+        const double2* w = cur + node * cap_in;
+        const int o = n_keep + 2 * j;  // first of the two outputs == first double2 of their window
+        double lo[2], hi[2];
+        fwd_stepR<L, 2>(taps, [&](int q) { return w[padr<R>(o + q)]; }, lo, hi);
+        double2* na = nxt + (2 * node) * cap_out + padr<R>(o >> 1);
+        na[0] = make_double2(lo[0], lo[1]);
+        na[cap_out] = make_double2(hi[0], hi[1]);
+      }
     }
-  } else {
-    // ---------------- resident mode ----------------
+    __syncthreads();
+    double2* t = cur; cur = nxt; nxt = t;
+    cap_in = cap_out;
+  }
+}
+
+// ---- resident mode --------------------------------------------------------------------------------
+template <int L, int R>
+__global__ void __launch_bounds__(512)
+k_wpt_fwd_res(const __grid_constant__ Taps taps, const WptFwdArgs a) {
+  extern __shared__ double2 smem2[];
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int m = a.m, h = a.h;
+  {
+
     const int G = a.G;
     const int64_t line0 = int64_t(blockIdx.x) * G;
     const int nlines = int(min(int64_t(G), a.lines - line0));
@@ -179,13 +216,14 @@ k_wpt_fwd(const __grid_constant__ Taps taps, const WptFwdArgs a) {
 // ---- host side ---------------------------------------------------------------------------------
 
 // Shared memory (bytes) of a tile-mode launch; also fills the per-buffer capacity.
-static size_t wpt_fwd_tile_smem(int L, int T, int m, int R, int* buf_cap) {
+static size_t wpt_fwd_tile_smem(int L, int T, int m, int R, int* buf_cap, int* caps = nullptr) {
   auto psize = [R](int n2) { return n2 + n2 / R + 2; };
   int cap = psize((T + ((1 << m) - 1) * (L - 2)) / 2 + R);  // level 0: one node
-  for (int k = 1; k < m; ++k) {                                   // levels kept in shared memory
+  for (int k = 1; k <= m; ++k) {                                  // levels kept in shared memory
     const int n_out = (T >> k) + ((1 << (m - k)) - 1) * (L - 2);
-    const int c = (1 << k) * psize(n_out / 2 + R);
-    if (c > cap) cap = c;
+    const int per_node = psize(n_out / 2 + R);
+    if (caps) caps[k] = per_node;
+    if (k < m && (1 << k) * per_node > cap) cap = (1 << k) * per_node;
   }
   *buf_cap = cap;
   return size_t(2) * cap * sizeof(double2);
@@ -205,10 +243,15 @@ template <int L, int R>
 static cudaError_t launch_LR(jwc_ctx* ctx, const Taps& taps, WptFwdArgs a, bool resident) {
   size_t smem;
   int64_t grid;
+  auto ilog2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
+  const int nthr = ctx->wpt_threads;
   if (!resident) {
-    if ((a.T >> a.m) < R) return cudaErrorInvalidValue;
-    smem = wpt_fwd_tile_smem(L, a.T, a.m, R, &a.buf_cap);
+    // T, h powers of two; at least one main warp beside the tail warp; steps of nthr keep the pad phase
+    if ((a.T >> a.m) < R || a.m > kMaxFuse || (a.T & (a.T - 1)) || nthr < 64 || nthr % 32) return cudaErrorInvalidValue;
+    smem = wpt_fwd_tile_smem(L, a.T, a.m, R, &a.buf_cap, a.cap);
     a.tiles_per_line = a.h / a.T;
+    a.lg_tpl = ilog2(a.tiles_per_line);
+    a.lg_T = ilog2(a.T);
     grid = a.lines * a.tiles_per_line;
   } else {
     a.buf_cap = padr_size<R>(max(1, a.h / 2));
@@ -216,13 +259,13 @@ static cudaError_t launch_LR(jwc_ctx* ctx, const Taps& taps, WptFwdArgs a, bool 
     grid = (a.lines + a.G - 1) / a.G;
   }
   if (grid > 0x7fffffff) return cudaErrorInvalidConfiguration;
-  auto kern = resident ? k_wpt_fwd<L, true, R> : k_wpt_fwd<L, false, R>;
+  auto kern = resident ? k_wpt_fwd_res<L, R> : k_wpt_fwd_tile<L, R>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
   }
   prof_begin(ctx, resident ? "k_wpt_fwd:resident" : "k_wpt_fwd:tile", double(a.lines) * a.h, a.m);
-  kern<<<int(grid), ctx->wpt_threads, smem, ctx->stream>>>(taps, a);
+  kern<<<int(grid), nthr, smem, ctx->stream>>>(taps, a);
   prof_end(ctx);
   ctx->launches++;
   return cudaGetLastError();

@@ -47,70 +47,100 @@ __device__ __forceinline__ void wrev_step(const Taps& taps, A2 a2, D2 d2, double
   }
 }
 
-template <int L, bool RESIDENT, int kRS>
+// ---- tile mode ------------------------------------------------------------------------------------
+// CTA = blockDim.x - 32 "main" threads + one tail warp.  At level k every parent owes T >> k slots the
+// tile keeps - T / (2 kRS) groups over all parents, a power of two, so the main warps are always full
+// and (parent, group) is a shift and a mask - plus F_k slots of left extension for the levels below
+// (none at level 1).  The extension goes to the tail warp, two slots per step, beside the main warps.
+template <int L, int kRS>
 __global__ void __launch_bounds__(512)
-k_wpt_rev(const __grid_constant__ Taps taps, const __grid_constant__ WptRevArgs a) {
+k_wpt_rev_tile(const __grid_constant__ Taps taps, const __grid_constant__ WptRevArgs a) {
   extern __shared__ double2 smem2[];
-  const int tid = threadIdx.x, nthr = blockDim.x;
-  const int m = a.m, h0 = a.h0;
-
-  if constexpr (!RESIDENT) {
-    // ---------------- tile mode ----------------
-    const int64_t line = blockIdx.x / a.tiles_per_line;
-    const int tile = int(blockIdx.x % a.tiles_per_line);
-    const int T = a.T;
-    const int t0 = tile * T;
-    double2* cur = smem2;
-    double2* nxt = smem2 + a.buf_cap;
-    {
-      // stage all 2^m leaf packets: local sample i of node j is slot O + i (periodic) of packet j
-      const int wm = h0 >> m;
-      const int O = (t0 >> m) - a.F[m] - a.ru8;
-      const int per_node = a.len[m] / 2;
-      const double* src = a.src + line * a.src_os;
-      const int total = per_node << m;
-      for (int it = tid; it < total; it += nthr) {
-        const int node = it / per_node, j2 = it - node * per_node;
-        cp_async16(&cur[node * a.cap[m] + pad2(j2)], src + int64_t(node) * wm + ((O + 2 * j2) & (wm - 1)));
-      }
-      cp_async_wait_all();
-      __syncthreads();
+  constexpr int lgRS = (kRS == 8) ? 3 : 2;
+  static_assert(kRS == 8 || kRS == 4, "kRS is 4 or 8");
+  const int tid = threadIdx.x, nthr = blockDim.x, nmain = nthr - 32;
+  const int m = a.m, h0 = a.h0, T = a.T;
+  const int64_t line = blockIdx.x >> a.lg_tpl;
+  const int tile = int(blockIdx.x) & (a.tiles_per_line - 1);
+  const int t0 = tile * T;
+  double2* cur = smem2;
+  double2* nxt = smem2 + a.buf_cap;
+  {
+    // stage all 2^m leaf packets: local sample i of node j is slot O + i (periodic) of packet j
+    const int wm = h0 >> m;
+    const int O = (t0 >> m) - a.F[m] - a.ru8;
+    const int per_node = a.len[m] / 2;
+    const double* src = a.src + line * a.src_os;
+    const int total = per_node << m;
+    int node = 0;
+    for (int it = tid, j2 = tid; it < total; it += nthr, j2 += nthr) {
+      while (j2 >= per_node) { j2 -= per_node; ++node; }
+      cp_async16(&cur[node * a.cap[m] + pad2(j2)], src + node * wm + ((O + 2 * j2) & (wm - 1)));
     }
-    for (int k = m; k >= 1; --k) {
-      const int groups = ((T >> k) + a.F[k]) / kRS;      // per parent node
-      const int base0 = 5 * a.g0[k];
-      const int cap_in = a.cap[k], cap_out = a.cap[k - 1];
-      const int items = groups << (k - 1);
-      // (parent, g) walk without a division: it = par * groups + g advances by nthr per step
-      for (int it = tid, par = tid / groups, g = tid - par * groups; it < items; it += nthr, g += nthr) {
-        while (g >= groups) { g -= groups; ++par; }
+    cp_async_wait_all();
+    __syncthreads();
+  }
+  for (int k = m; k >= 1; --k) {
+    const int cap_in = a.cap[k], cap_out = a.cap[k - 1];
+    const int g0 = a.g0[k];
+    if (tid < nmain) {
+      const int lg_gpp = a.lg_T - k - lgRS;  // kept groups per parent = (T >> k) / kRS
+      const int gl = a.F[k] >> lgRS;         // groups of left extension in front of them
+      for (int it = tid; it < ((T >> 1) >> lgRS); it += nmain) {
+        const int par = it >> lg_gpp, g = gl + (it & ((1 << lg_gpp) - 1));
         double t[2 * kRS];
         if constexpr (kRS == 8) {
-          const double2* A = cur + (2 * par) * cap_in + base0 + 5 * g;   // pad2(4g'+3-w) = 5g' + (3-w) + floor((3-w)/4)
+          const double2* A = cur + (2 * par) * cap_in + 5 * (g0 + g);  // pad2(4g'+3-w) = 5g' + (3-w) + floor((3-w)/4)
           const double2* D = A + cap_in;
           wrev_step<L, 8>(taps, [&](int w) { return A[(3 - w) + ((3 - w) >> 2)]; },
                           [&](int w) { return D[(3 - w) + ((3 - w) >> 2)]; }, t);
         } else {
           const double2* A = cur + (2 * par) * cap_in;
           const double2* D = A + cap_in;
-          const int c = 4 * a.g0[k] + (kRS / 2) * g + kRS / 2 - 1;
+          const int c = 4 * g0 + (kRS / 2) * g + kRS / 2 - 1;
           wrev_step<L, kRS>(taps, [&](int w) { return A[pad2(c - w)]; }, [&](int w) { return D[pad2(c - w)]; }, t);
         }
         if (k > 1) {
-          double2* Y = nxt + par * cap_out;
+          // pad2(kRS g + e) == kRS g + (kRS / 4) g + e + (e >> 2)
+          double2* Y = nxt + par * cap_out + (kRS + kRS / 4) * g;
 #pragma unroll
-          for (int e = 0; e < kRS; ++e) Y[pad2(kRS * g + e)] = make_double2(t[2 * e], t[2 * e + 1]);
+          for (int e = 0; e < kRS; ++e) Y[e + (e >> 2)] = make_double2(t[2 * e], t[2 * e + 1]);
         } else {
-          double* y = a.dst + line * a.dst_os + t0 + 2 * kRS * g;
+          double* y = a.dst + line * a.dst_os + t0 + 2 * kRS * (g - gl);
 #pragma unroll
           for (int e = 0; e < kRS / 2; ++e) st_global_v4(y + 4 * e, t[4 * e], t[4 * e + 1], t[4 * e + 2], t[4 * e + 3]);
         }
       }
-      __syncthreads();
-      double2* tmp = cur; cur = nxt; nxt = tmp;
+    } else if (k > 1) {
+      const int per_par = a.F[k] >> 1;  // tail steps per parent (F_k is a multiple of 8)
+      const int items = per_par << (k - 1);
+      int par = 0;
+      for (int it = tid - nmain, g = it; it < items; it += 32, g += 32) {
+        while (g >= per_par) { g -= per_par; ++par; }
+        const double2* A = cur + (2 * par) * cap_in;
+        const double2* D = A + cap_in;
+        const int c = 4 * g0 + g;
+        double t[4];
+        wrev_step<L, 2>(taps, [&](int w) { return A[pad2(c - w)]; }, [&](int w) { return D[pad2(c - w)]; }, t);
+        double2* Y = nxt + par * cap_out;
+        Y[pad2(2 * g)] = make_double2(t[0], t[1]);
+        Y[pad2(2 * g + 1)] = make_double2(t[2], t[3]);
+      }
     }
-  } else {
-    // ---------------- resident mode ----------------
+    __syncthreads();
+    double2* tmp = cur; cur = nxt; nxt = tmp;
+  }
+}
+
+// ---- resident mode --------------------------------------------------------------------------------
+template <int L, int kRS>
+__global__ void __launch_bounds__(512)
+k_wpt_rev_res(const __grid_constant__ Taps taps, const __grid_constant__ WptRevArgs a) {
+  extern __shared__ double2 smem2[];
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int m = a.m, h0 = a.h0;
+  {
+
     const int G = a.G;
     const int64_t line0 = int64_t(blockIdx.x) * G;
     const int nlines = int(min(int64_t(G), a.lines - line0));
@@ -230,9 +260,14 @@ static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, WptRevArgs a, bool r
   size_t smem;
   int64_t grid;
   if (!resident) {
-    if (a.m < 1 || a.m > kMaxFuse || (a.T >> a.m) < 8) return cudaErrorInvalidValue;
+    if (a.m < 1 || a.m > kMaxFuse || (a.T >> a.m) < 8 || (a.T & (a.T - 1)) || ctx->wpt_threads < 64 ||
+        ctx->wpt_threads % 32)
+      return cudaErrorInvalidValue;
     smem = wpt_rev_tile_geometry(L, a);
     a.tiles_per_line = a.h0 / a.T;
+    auto ilog2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
+    a.lg_tpl = ilog2(a.tiles_per_line);
+    a.lg_T = ilog2(a.T);
     grid = a.lines * a.tiles_per_line;
   } else {
     a.buf_cap = pad2_size(max(1, a.h0 / 2));
@@ -240,8 +275,8 @@ static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, WptRevArgs a, bool r
     grid = (a.lines + a.G - 1) / a.G;
   }
   if (grid > 0x7fffffff) return cudaErrorInvalidConfiguration;
-  auto kern = resident ? (ctx->wpt_rs == 4 ? k_wpt_rev<L, true, 4> : k_wpt_rev<L, true, 8>)
-                       : (ctx->wpt_rs == 4 ? k_wpt_rev<L, false, 4> : k_wpt_rev<L, false, 8>);
+  auto kern = resident ? (ctx->wpt_rs == 4 ? k_wpt_rev_res<L, 4> : k_wpt_rev_res<L, 8>)
+                       : (ctx->wpt_rs == 4 ? k_wpt_rev_tile<L, 4> : k_wpt_rev_tile<L, 8>);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
