@@ -20,6 +20,10 @@
 #include "jwc_fused.cuh"
 #include "jwc_kernels.cuh"
 
+#ifndef JWC_WPT_TAIL_WARP
+#define JWC_WPT_TAIL_WARP 1
+#endif
+
 namespace jwc {
 
 // Layout of this kernel's shared-memory lines: one pad slot per R double2, so a thread that
@@ -37,18 +41,19 @@ template <int R> __device__ __forceinline__ void lscalar_store(double2* buf, int
 }
 
 // ---- tile mode ------------------------------------------------------------------------------------
-// CTA = blockDim.x - 32 "main" threads + one tail warp.  At every level the T/2 outputs (per filter) the
-// tile keeps are exactly T / (2R) groups of R, a power of two, so the main warps are always full and
-// the (node, group) split of an item is a shift and a mask.  The halo outputs a node owes the levels
-// below ((2^(m-k) - 1)(L - 2) per node, none at the last level) go to the tail warp, two per step: it
-// runs beside the main warps instead of costing every level one more nearly empty R-wide step.
+// At every level the T/2 outputs (per filter) the tile keeps are exactly T / (2R) groups of R, a power
+// of two, so the warps are always full and the (node, group) split of an item is a shift and a mask.
+// The halo outputs a node owes the levels below ((2^(m-k) - 1)(L - 2) per node, none at the last
+// level) are a separate short step, two outputs per lane, instead of one more nearly empty R-wide step
+// for every warp; JWC_WPT_TAIL_WARP selects who runs it: a dedicated extra warp (1) or one of the
+// main warps, rotating with the CTA and the level so that no SM sub-partition collects all of it (0).
 template <int L, int R>
 __global__ void __launch_bounds__(512)
 k_wpt_fwd_tile(const __grid_constant__ Taps taps, const __grid_constant__ WptFwdArgs a) {
   extern __shared__ double2 smem2[];
   constexpr int lgR = (R == 8) ? 3 : 2;
   static_assert(R == 8 || R == 4, "R is 4 or 8");
-  const int tid = threadIdx.x, nthr = blockDim.x, nmain = nthr - 32;
+  const int tid = threadIdx.x, nthr = blockDim.x, nmain = nthr - 32 * JWC_WPT_TAIL_WARP;
   const int m = a.m, h = a.h, T = a.T;
   const int64_t line = blockIdx.x >> a.lg_tpl;
   const int tile = int(blockIdx.x) & (a.tiles_per_line - 1);
@@ -102,12 +107,14 @@ k_wpt_fwd_tile(const __grid_constant__ Taps taps, const __grid_constant__ WptFwd
           }
         }
       }
-    } else if (!last) {
+    }
+    const int tail_warp = JWC_WPT_TAIL_WARP ? (nmain >> 5) : int((blockIdx.x + k) % unsigned(nthr >> 5));
+    if (!last && (tid >> 5) == tail_warp) {
       const int n_keep = T >> k;
       const int per_node = (((1 << (m - k)) - 1) * (L - 2)) >> 1;  // halo steps per node (L - 2 is even)
       const int items = per_node << (k - 1);
       int node = 0;
-      for (int it = tid - nmain, j = it; it < items; it += 32, j += 32) {
+      for (int it = tid & 31, j = it; it < items; it += 32, j += 32) {
         while (j >= per_node) { j -= per_node; ++node; }
         const double2* w = cur + node * cap_in;
         const int o = n_keep + 2 * j;  // first of the two outputs == first double2 of their window
@@ -247,7 +254,8 @@ static cudaError_t launch_LR(jwc_ctx* ctx, const Taps& taps, WptFwdArgs a, bool 
   const int nthr = ctx->wpt_threads;
   if (!resident) {
     // T, h powers of two; at least one main warp beside the tail warp; steps of nthr keep the pad phase
-    if ((a.T >> a.m) < R || a.m > kMaxFuse || (a.T & (a.T - 1)) || nthr < 64 || nthr % 32) return cudaErrorInvalidValue;
+    if ((a.T >> a.m) < R || a.m > kMaxFuse || (a.T & (a.T - 1)) || nthr < 32 + 32 * JWC_WPT_TAIL_WARP || nthr % 32)
+      return cudaErrorInvalidValue;
     smem = wpt_fwd_tile_smem(L, a.T, a.m, R, &a.buf_cap, a.cap);
     a.tiles_per_line = a.h / a.T;
     a.lg_tpl = ilog2(a.tiles_per_line);

@@ -16,6 +16,10 @@
 #include "jwc_fused.cuh"
 #include "jwc_kernels.cuh"
 
+#ifndef JWC_WPT_TAIL_WARP
+#define JWC_WPT_TAIL_WARP 1
+#endif
+
 namespace jwc {
 
 // RS consecutive slots -> t[2 RS]; a2(w)/d2(w) = double2 (RS/2 g' + RS/2 - 1 - w); see jwc_fwt_rev.cu
@@ -48,17 +52,18 @@ __device__ __forceinline__ void wrev_step(const Taps& taps, A2 a2, D2 d2, double
 }
 
 // ---- tile mode ------------------------------------------------------------------------------------
-// CTA = blockDim.x - 32 "main" threads + one tail warp.  At level k every parent owes T >> k slots the
-// tile keeps - T / (2 kRS) groups over all parents, a power of two, so the main warps are always full
-// and (parent, group) is a shift and a mask - plus F_k slots of left extension for the levels below
-// (none at level 1).  The extension goes to the tail warp, two slots per step, beside the main warps.
+// At level k every parent owes T >> k slots the tile keeps - T / (2 kRS) groups over all parents, a
+// power of two, so the warps are always full and (parent, group) is a shift and a mask - plus F_k
+// slots of left extension for the levels below (none at level 1).  The extension is a separate short
+// step, two slots per lane, run by a dedicated extra warp (JWC_WPT_TAIL_WARP = 1) or by one of the main
+// warps, rotating with the CTA and the level (0); see jwc_wpt_fwd.cu.
 template <int L, int kRS>
 __global__ void __launch_bounds__(512)
 k_wpt_rev_tile(const __grid_constant__ Taps taps, const __grid_constant__ WptRevArgs a) {
   extern __shared__ double2 smem2[];
   constexpr int lgRS = (kRS == 8) ? 3 : 2;
   static_assert(kRS == 8 || kRS == 4, "kRS is 4 or 8");
-  const int tid = threadIdx.x, nthr = blockDim.x, nmain = nthr - 32;
+  const int tid = threadIdx.x, nthr = blockDim.x, nmain = nthr - 32 * JWC_WPT_TAIL_WARP;
   const int m = a.m, h0 = a.h0, T = a.T;
   const int64_t line = blockIdx.x >> a.lg_tpl;
   const int tile = int(blockIdx.x) & (a.tiles_per_line - 1);
@@ -103,19 +108,38 @@ k_wpt_rev_tile(const __grid_constant__ Taps taps, const __grid_constant__ WptRev
         if (k > 1) {
           // pad2(kRS g + e) == kRS g + (kRS / 4) g + e + (e >> 2)
           double2* Y = nxt + par * cap_out + (kRS + kRS / 4) * g;
+          if constexpr (kRS == 8) {
+            // the lanes of an STS.128 phase are 10 slots apart - groups g and g + 4 share a bank group.
+            // Lanes with bit 2 of g set store their upper four slots first: slot e ^ 4 sits 5 padded
+            // slots from slot e, an odd distance, which separates the two halves of the phase.
+            const bool rot = (g >> 2) & 1;
+            double2* Ylo = Y + (rot ? 5 : 0);
+            double2* Yhi = Y - (rot ? 5 : 0);
 #pragma unroll
-          for (int e = 0; e < kRS; ++e) Y[e + (e >> 2)] = make_double2(t[2 * e], t[2 * e + 1]);
+            for (int e = 0; e < 4; ++e) {
+              Ylo[e] = make_double2(rot ? t[2 * e + 8] : t[2 * e], rot ? t[2 * e + 9] : t[2 * e + 1]);
+            }
+#pragma unroll
+            for (int e = 4; e < 8; ++e) {
+              Yhi[e + 1] = make_double2(rot ? t[2 * e - 8] : t[2 * e], rot ? t[2 * e - 7] : t[2 * e + 1]);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < kRS; ++e) Y[e + (e >> 2)] = make_double2(t[2 * e], t[2 * e + 1]);
+          }
         } else {
           double* y = a.dst + line * a.dst_os + t0 + 2 * kRS * (g - gl);
 #pragma unroll
           for (int e = 0; e < kRS / 2; ++e) st_global_v4(y + 4 * e, t[4 * e], t[4 * e + 1], t[4 * e + 2], t[4 * e + 3]);
         }
       }
-    } else if (k > 1) {
+    }
+    const int tail_warp = JWC_WPT_TAIL_WARP ? (nmain >> 5) : int((blockIdx.x + k) % unsigned(nthr >> 5));
+    if (k > 1 && (tid >> 5) == tail_warp) {
       const int per_par = a.F[k] >> 1;  // tail steps per parent (F_k is a multiple of 8)
       const int items = per_par << (k - 1);
       int par = 0;
-      for (int it = tid - nmain, g = it; it < items; it += 32, g += 32) {
+      for (int it = tid & 31, g = it; it < items; it += 32, g += 32) {
         while (g >= per_par) { g -= per_par; ++par; }
         const double2* A = cur + (2 * par) * cap_in;
         const double2* D = A + cap_in;
@@ -260,7 +284,7 @@ static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, WptRevArgs a, bool r
   size_t smem;
   int64_t grid;
   if (!resident) {
-    if (a.m < 1 || a.m > kMaxFuse || (a.T >> a.m) < 8 || (a.T & (a.T - 1)) || ctx->wpt_threads < 64 ||
+    if (a.m < 1 || a.m > kMaxFuse || (a.T >> a.m) < 8 || (a.T & (a.T - 1)) || ctx->wpt_threads < 32 + 32 * JWC_WPT_TAIL_WARP ||
         ctx->wpt_threads % 32)
       return cudaErrorInvalidValue;
     smem = wpt_rev_tile_geometry(L, a);
