@@ -108,6 +108,7 @@ extern "C" int jwc_create(jwc_ctx** out, int device) {
     get("str_rev_threads", &ctx->str_rev_threads);
     get("str_tma", &ctx->str_tma);
     get("wpt_threads", &ctx->wpt_threads);
+    get("wpt_inplace", &ctx->wpt_inplace);
   }
   *out = ctx;
   return JWC_OK;

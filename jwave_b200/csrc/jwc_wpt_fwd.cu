@@ -47,7 +47,7 @@ template <int R> __device__ __forceinline__ void lscalar_store(double2* buf, int
 // level) are a separate short step, two outputs per lane, instead of one more nearly empty R-wide step
 // for every warp; JWC_WPT_TAIL_WARP selects who runs it: a dedicated extra warp (1) or one of the
 // main warps, rotating with the CTA and the level so that no SM sub-partition collects all of it (0).
-template <int L, int R>
+template <int L, int R, bool INPLACE>
 __global__ void __launch_bounds__(512)
 k_wpt_fwd_tile(const __grid_constant__ Taps taps, const __grid_constant__ WptFwdArgs a) {
   extern __shared__ double2 smem2[];
@@ -59,7 +59,7 @@ k_wpt_fwd_tile(const __grid_constant__ Taps taps, const __grid_constant__ WptFwd
   const int tile = int(blockIdx.x) & (a.tiles_per_line - 1);
   const int base = tile * T;
   double2* cur = smem2;
-  double2* nxt = smem2 + a.buf_cap;
+  double2* nxt = INPLACE ? smem2 : smem2 + a.buf_cap;
   {
     // stage the tile and its right halo; only the last tile of a line wraps (once: halo <= T / 4 < h).
     // nthr is a multiple of R, so a step of nthr double2 is a constant step through the padded layout.
@@ -78,6 +78,66 @@ k_wpt_fwd_tile(const __grid_constant__ Taps taps, const __grid_constant__ WptFwd
   }
 
   int cap_in = 0;  // per-node capacity of the level being read (one node at level 0)
+  if constexpr (INPLACE) {
+    // One item per thread and level (the launcher checks it): the results wait in registers until every
+    // window of the level has been read, then overwrite the level's input.  One buffer instead of two
+    // halves the shared memory of a CTA - more CTAs, i.e. more warps in their FMA phase, per SM - for
+    // one more barrier per level.
+    for (int k = 1; k <= m; ++k) {
+      const int cap_out = a.cap[k];
+      const bool last = (k == m);
+      double lo[R], hi[R];
+      int node = 0, g = 0, o = 0;
+      bool has = false;
+      if (tid < nmain) {
+        const int lg_gpn = a.lg_T - k - lgR;
+        node = tid >> lg_gpn;
+        g = tid & ((1 << lg_gpn) - 1);
+        const double2* w = cur + node * cap_in + (R + 1) * g;
+        fwd_stepR<L, R>(taps, [&](int q) { return w[q + q / R]; }, lo, hi);
+      } else if (!last) {
+        const int per_node = (((1 << (m - k)) - 1) * (L - 2)) >> 1;
+        int j = tid - nmain;
+        has = j < (per_node << (k - 1));
+        if (has) {
+          while (j >= per_node) { j -= per_node; ++node; }
+          const double2* w = cur + node * cap_in;
+          o = (T >> k) + 2 * j;
+          double l2[2], h2[2];
+          fwd_stepR<L, 2>(taps, [&](int q) { return w[padr<R>(o + q)]; }, l2, h2);
+          lo[0] = l2[0]; lo[1] = l2[1]; hi[0] = h2[0]; hi[1] = h2[1];
+        }
+      }
+      if (last) {
+        if (tid < nmain) {
+          const int leaf = h >> m;
+          double* pa = a.dst + line * a.dst_os + int64_t(2 * node) * leaf + (base >> m) + R * g;
+#pragma unroll
+          for (int e = 0; e < R / 4; ++e) {
+            st_global_v4(pa + 4 * e, lo[4 * e], lo[4 * e + 1], lo[4 * e + 2], lo[4 * e + 3]);
+            st_global_v4(pa + leaf + 4 * e, hi[4 * e], hi[4 * e + 1], hi[4 * e + 2], hi[4 * e + 3]);
+          }
+        }
+        break;
+      }
+      __syncthreads();
+      if (tid < nmain) {
+        double2* na = cur + (2 * node) * cap_out + (R / 2) * g + (g >> 1);
+        double2* nd = na + cap_out;
+#pragma unroll
+        for (int e = 0; e < R / 2; ++e) {
+          na[e] = make_double2(lo[2 * e], lo[2 * e + 1]);
+          nd[e] = make_double2(hi[2 * e], hi[2 * e + 1]);
+        }
+      } else if (has) {
+        double2* na = cur + (2 * node) * cap_out + padr<R>(o >> 1);
+        na[0] = make_double2(lo[0], lo[1]);
+        na[cap_out] = make_double2(hi[0], hi[1]);
+      }
+      __syncthreads();
+      cap_in = cap_out;
+    }
+  } else {
   for (int k = 1; k <= m; ++k) {
     const int cap_out = a.cap[k];
     const bool last = (k == m);
@@ -128,6 +188,7 @@ k_wpt_fwd_tile(const __grid_constant__ Taps taps, const __grid_constant__ WptFwd
     __syncthreads();
     double2* t = cur; cur = nxt; nxt = t;
     cap_in = cap_out;
+  }
   }
 }
 
@@ -252,11 +313,16 @@ static cudaError_t launch_LR(jwc_ctx* ctx, const Taps& taps, WptFwdArgs a, bool 
   int64_t grid;
   auto ilog2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
   const int nthr = ctx->wpt_threads;
+  bool inplace = false;
   if (!resident) {
     // T, h powers of two; at least one main warp beside the tail warp; steps of nthr keep the pad phase
     if ((a.T >> a.m) < R || a.m > kMaxFuse || (a.T & (a.T - 1)) || nthr < 32 + 32 * JWC_WPT_TAIL_WARP || nthr % 32)
       return cudaErrorInvalidValue;
     smem = wpt_fwd_tile_smem(L, a.T, a.m, R, &a.buf_cap, a.cap);
+    inplace = JWC_WPT_TAIL_WARP && ctx->wpt_inplace && nthr - 32 == (a.T / 2) / R;
+    for (int k = 1; k < a.m; ++k)  // tail steps of a level: one per lane of the tail warp
+      if (((((1 << (a.m - k)) - 1) * (L - 2)) >> 1) << (k - 1) > 32) inplace = false;
+    if (inplace) smem /= 2;
     a.tiles_per_line = a.h / a.T;
     a.lg_tpl = ilog2(a.tiles_per_line);
     a.lg_T = ilog2(a.T);
@@ -267,7 +333,7 @@ static cudaError_t launch_LR(jwc_ctx* ctx, const Taps& taps, WptFwdArgs a, bool 
     grid = (a.lines + a.G - 1) / a.G;
   }
   if (grid > 0x7fffffff) return cudaErrorInvalidConfiguration;
-  auto kern = resident ? k_wpt_fwd_res<L, R> : k_wpt_fwd_tile<L, R>;
+  auto kern = resident ? k_wpt_fwd_res<L, R> : inplace ? k_wpt_fwd_tile<L, R, true> : k_wpt_fwd_tile<L, R, false>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;

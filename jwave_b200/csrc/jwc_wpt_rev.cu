@@ -57,7 +57,7 @@ __device__ __forceinline__ void wrev_step(const Taps& taps, A2 a2, D2 d2, double
 // slots of left extension for the levels below (none at level 1).  The extension is a separate short
 // step, two slots per lane, run by a dedicated extra warp (JWC_WPT_TAIL_WARP = 1) or by one of the main
 // warps, rotating with the CTA and the level (0); see jwc_wpt_fwd.cu.
-template <int L, int kRS>
+template <int L, int kRS, bool INPLACE>
 __global__ void __launch_bounds__(512)
 k_wpt_rev_tile(const __grid_constant__ Taps taps, const __grid_constant__ WptRevArgs a) {
   extern __shared__ double2 smem2[];
@@ -69,7 +69,7 @@ k_wpt_rev_tile(const __grid_constant__ Taps taps, const __grid_constant__ WptRev
   const int tile = int(blockIdx.x) & (a.tiles_per_line - 1);
   const int t0 = tile * T;
   double2* cur = smem2;
-  double2* nxt = smem2 + a.buf_cap;
+  double2* nxt = INPLACE ? smem2 : smem2 + a.buf_cap;
   {
     // stage all 2^m leaf packets: local sample i of node j is slot O + i (periodic) of packet j
     const int wm = h0 >> m;
@@ -85,74 +85,122 @@ k_wpt_rev_tile(const __grid_constant__ Taps taps, const __grid_constant__ WptRev
     cp_async_wait_all();
     __syncthreads();
   }
-  for (int k = m; k >= 1; --k) {
-    const int cap_in = a.cap[k], cap_out = a.cap[k - 1];
-    const int g0 = a.g0[k];
-    if (tid < nmain) {
-      const int lg_gpp = a.lg_T - k - lgRS;  // kept groups per parent = (T >> k) / kRS
-      const int gl = a.F[k] >> lgRS;         // groups of left extension in front of them
-      for (int it = tid; it < ((T >> 1) >> lgRS); it += nmain) {
-        const int par = it >> lg_gpp, g = gl + (it & ((1 << lg_gpp) - 1));
-        double t[2 * kRS];
-        if constexpr (kRS == 8) {
-          const double2* A = cur + (2 * par) * cap_in + 5 * (g0 + g);  // pad2(4g'+3-w) = 5g' + (3-w) + floor((3-w)/4)
-          const double2* D = A + cap_in;
-          wrev_step<L, 8>(taps, [&](int w) { return A[(3 - w) + ((3 - w) >> 2)]; },
-                          [&](int w) { return D[(3 - w) + ((3 - w) >> 2)]; }, t);
-        } else {
-          const double2* A = cur + (2 * par) * cap_in;
-          const double2* D = A + cap_in;
-          const int c = 4 * g0 + (kRS / 2) * g + kRS / 2 - 1;
-          wrev_step<L, kRS>(taps, [&](int w) { return A[pad2(c - w)]; }, [&](int w) { return D[pad2(c - w)]; }, t);
-        }
-        if (k > 1) {
-          // pad2(kRS g + e) == kRS g + (kRS / 4) g + e + (e >> 2)
-          double2* Y = nxt + par * cap_out + (kRS + kRS / 4) * g;
-          if constexpr (kRS == 8) {
-            // the lanes of an STS.128 phase are 10 slots apart - groups g and g + 4 share a bank group.
-            // Lanes with bit 2 of g set store their upper four slots first: slot e ^ 4 sits 5 padded
-            // slots from slot e, an odd distance, which separates the two halves of the phase.
-            const bool rot = (g >> 2) & 1;
-            double2* Ylo = Y + (rot ? 5 : 0);
-            double2* Yhi = Y - (rot ? 5 : 0);
+  // one group of kRS slots of parent `par`: t[2 kRS] from the children's windows in `cur`
+  auto main_step = [&](int k, int par, int g, double (&t)[2 * kRS]) {
+    const int cap_in = a.cap[k];
+    if constexpr (kRS == 8) {
+      const double2* A = cur + (2 * par) * cap_in + 5 * (a.g0[k] + g);  // pad2(4g'+3-w) = 5g' + (3-w) + floor((3-w)/4)
+      const double2* D = A + cap_in;
+      wrev_step<L, 8>(taps, [&](int w) { return A[(3 - w) + ((3 - w) >> 2)]; },
+                      [&](int w) { return D[(3 - w) + ((3 - w) >> 2)]; }, t);
+    } else {
+      const double2* A = cur + (2 * par) * cap_in;
+      const double2* D = A + cap_in;
+      const int c = 4 * a.g0[k] + (kRS / 2) * g + kRS / 2 - 1;
+      wrev_step<L, kRS>(taps, [&](int w) { return A[pad2(c - w)]; }, [&](int w) { return D[pad2(c - w)]; }, t);
+    }
+  };
+  auto main_store = [&](int k, int par, int g, int gl, const double (&t)[2 * kRS]) {
+    if (k > 1) {
+      // pad2(kRS g + e) == kRS g + (kRS / 4) g + e + (e >> 2)
+      double2* Y = nxt + par * a.cap[k - 1] + (kRS + kRS / 4) * g;
+      if constexpr (kRS == 8) {
+        // the lanes of an STS.128 phase are 10 slots apart - groups g and g + 4 share a bank group.
+        // Lanes with bit 2 of g set store their upper four slots first: slot e ^ 4 sits 5 padded
+        // slots from slot e, an odd distance, which separates the two halves of the phase.
+        const bool rot = (g >> 2) & 1;
+        double2* Ylo = Y + (rot ? 5 : 0);
+        double2* Yhi = Y - (rot ? 5 : 0);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              Ylo[e] = make_double2(rot ? t[2 * e + 8] : t[2 * e], rot ? t[2 * e + 9] : t[2 * e + 1]);
-            }
+        for (int e = 0; e < 4; ++e)
+          Ylo[e] = make_double2(rot ? t[2 * e + 8] : t[2 * e], rot ? t[2 * e + 9] : t[2 * e + 1]);
 #pragma unroll
-            for (int e = 4; e < 8; ++e) {
-              Yhi[e + 1] = make_double2(rot ? t[2 * e - 8] : t[2 * e], rot ? t[2 * e - 7] : t[2 * e + 1]);
-            }
-          } else {
+        for (int e = 4; e < 8; ++e)
+          Yhi[e + 1] = make_double2(rot ? t[2 * e - 8] : t[2 * e], rot ? t[2 * e - 7] : t[2 * e + 1]);
+      } else {
 #pragma unroll
-            for (int e = 0; e < kRS; ++e) Y[e + (e >> 2)] = make_double2(t[2 * e], t[2 * e + 1]);
-          }
-        } else {
-          double* y = a.dst + line * a.dst_os + t0 + 2 * kRS * (g - gl);
+        for (int e = 0; e < kRS; ++e) Y[e + (e >> 2)] = make_double2(t[2 * e], t[2 * e + 1]);
+      }
+    } else {
+      double* y = a.dst + line * a.dst_os + t0 + 2 * kRS * (g - gl);
 #pragma unroll
-          for (int e = 0; e < kRS / 2; ++e) st_global_v4(y + 4 * e, t[4 * e], t[4 * e + 1], t[4 * e + 2], t[4 * e + 3]);
+      for (int e = 0; e < kRS / 2; ++e) st_global_v4(y + 4 * e, t[4 * e], t[4 * e + 1], t[4 * e + 2], t[4 * e + 3]);
+    }
+  };
+  // two slots of left extension (tail step number g of parent `par`)
+  auto tail_step = [&](int k, int par, int g, double (&t)[4]) {
+    const double2* A = cur + (2 * par) * a.cap[k];
+    const double2* D = A + a.cap[k];
+    const int c = 4 * a.g0[k] + g;
+    wrev_step<L, 2>(taps, [&](int w) { return A[pad2(c - w)]; }, [&](int w) { return D[pad2(c - w)]; }, t);
+  };
+  auto tail_store = [&](int k, int par, int g, const double (&t)[4]) {
+    double2* Y = nxt + par * a.cap[k - 1];
+    Y[pad2(2 * g)] = make_double2(t[0], t[1]);
+    Y[pad2(2 * g + 1)] = make_double2(t[2], t[3]);
+  };
+
+  if constexpr (INPLACE) {
+    // One item per thread and level (the launcher checks it): results wait in registers until every
+    // window of the level has been read, then overwrite the level's input - one buffer instead of two,
+    // more CTAs per SM, one more barrier per level (see jwc_wpt_fwd.cu).
+    for (int k = m; k >= 1; --k) {
+      double t[2 * kRS];
+      int par = 0, g = 0;
+      bool has = false;
+      const int gl = a.F[k] >> lgRS;
+      if (tid < nmain) {
+        const int lg_gpp = a.lg_T - k - lgRS;
+        par = tid >> lg_gpp;
+        g = gl + (tid & ((1 << lg_gpp) - 1));
+        main_step(k, par, g, t);
+      } else if (k > 1) {
+        const int per_par = a.F[k] >> 1;
+        g = tid - nmain;
+        has = g < (per_par << (k - 1));
+        if (has) {
+          while (g >= per_par) { g -= per_par; ++par; }
+          double t4[4];
+          tail_step(k, par, g, t4);
+          t[0] = t4[0]; t[1] = t4[1]; t[2] = t4[2]; t[3] = t4[3];
         }
       }
-    }
-    const int tail_warp = JWC_WPT_TAIL_WARP ? (nmain >> 5) : int((blockIdx.x + k) % unsigned(nthr >> 5));
-    if (k > 1 && (tid >> 5) == tail_warp) {
-      const int per_par = a.F[k] >> 1;  // tail steps per parent (F_k is a multiple of 8)
-      const int items = per_par << (k - 1);
-      int par = 0;
-      for (int it = tid & 31, g = it; it < items; it += 32, g += 32) {
-        while (g >= per_par) { g -= per_par; ++par; }
-        const double2* A = cur + (2 * par) * cap_in;
-        const double2* D = A + cap_in;
-        const int c = 4 * g0 + g;
-        double t[4];
-        wrev_step<L, 2>(taps, [&](int w) { return A[pad2(c - w)]; }, [&](int w) { return D[pad2(c - w)]; }, t);
-        double2* Y = nxt + par * cap_out;
-        Y[pad2(2 * g)] = make_double2(t[0], t[1]);
-        Y[pad2(2 * g + 1)] = make_double2(t[2], t[3]);
+      if (k > 1) __syncthreads();
+      if (tid < nmain) {
+        main_store(k, par, g, gl, t);
+      } else if (has) {
+        const double t4[4] = {t[0], t[1], t[2], t[3]};
+        tail_store(k, par, g, t4);
       }
+      if (k > 1) __syncthreads();
     }
-    __syncthreads();
-    double2* tmp = cur; cur = nxt; nxt = tmp;
+  } else {
+    for (int k = m; k >= 1; --k) {
+      if (tid < nmain) {
+        const int lg_gpp = a.lg_T - k - lgRS;  // kept groups per parent = (T >> k) / kRS
+        const int gl = a.F[k] >> lgRS;         // groups of left extension in front of them
+        for (int it = tid; it < ((T >> 1) >> lgRS); it += nmain) {
+          const int par = it >> lg_gpp, g = gl + (it & ((1 << lg_gpp) - 1));
+          double t[2 * kRS];
+          main_step(k, par, g, t);
+          main_store(k, par, g, gl, t);
+        }
+      }
+      const int tail_warp = JWC_WPT_TAIL_WARP ? (nmain >> 5) : int((blockIdx.x + k) % unsigned(nthr >> 5));
+      if (k > 1 && (tid >> 5) == tail_warp) {
+        const int per_par = a.F[k] >> 1;  // tail steps per parent (F_k is a multiple of 8)
+        const int items = per_par << (k - 1);
+        int par = 0;
+        for (int it = tid & 31, g = it; it < items; it += 32, g += 32) {
+          while (g >= per_par) { g -= per_par; ++par; }
+          double t[4];
+          tail_step(k, par, g, t);
+          tail_store(k, par, g, t);
+        }
+      }
+      __syncthreads();
+      double2* tmp = cur; cur = nxt; nxt = tmp;
+    }
   }
 }
 
@@ -283,11 +331,16 @@ template <int L>
 static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, WptRevArgs a, bool resident) {
   size_t smem;
   int64_t grid;
+  bool inplace = false;
   if (!resident) {
     if (a.m < 1 || a.m > kMaxFuse || (a.T >> a.m) < 8 || (a.T & (a.T - 1)) || ctx->wpt_threads < 32 + 32 * JWC_WPT_TAIL_WARP ||
         ctx->wpt_threads % 32)
       return cudaErrorInvalidValue;
     smem = wpt_rev_tile_geometry(L, a);
+    inplace = JWC_WPT_TAIL_WARP && ctx->wpt_inplace && ctx->wpt_threads - 32 == (a.T / 2) / (ctx->wpt_rs == 4 ? 4 : 8);
+    for (int k = 2; k <= a.m; ++k)  // tail steps of a level: one per lane of the tail warp
+      if (((a.F[k] >> 1) << (k - 1)) > 32) inplace = false;
+    if (inplace) smem /= 2;
     a.tiles_per_line = a.h0 / a.T;
     auto ilog2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
     a.lg_tpl = ilog2(a.tiles_per_line);
@@ -300,7 +353,8 @@ static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, WptRevArgs a, bool r
   }
   if (grid > 0x7fffffff) return cudaErrorInvalidConfiguration;
   auto kern = resident ? (ctx->wpt_rs == 4 ? k_wpt_rev_res<L, 4> : k_wpt_rev_res<L, 8>)
-                       : (ctx->wpt_rs == 4 ? k_wpt_rev_tile<L, 4> : k_wpt_rev_tile<L, 8>);
+                       : inplace ? (ctx->wpt_rs == 4 ? k_wpt_rev_tile<L, 4, true> : k_wpt_rev_tile<L, 8, true>)
+                                 : (ctx->wpt_rs == 4 ? k_wpt_rev_tile<L, 4, false> : k_wpt_rev_tile<L, 8, false>);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
