@@ -11,23 +11,26 @@ import math
 
 import numpy as np
 
+from ._taps_bior import BIOR_TAPS
 from ._taps_literal import LITERAL_TAPS
 
 
 class Wavelet:
     """Wavelet.java:38-219: name, wavelengths and the four filters (getters return copies)."""
 
-    def __init__(self, name, scalingDeCom, waveletDeCom=None):
+    def __init__(self, name, scalingDeCom, waveletDeCom=None, scalingReCon=None, waveletReCon=None):
         self._name = name
         self._transformWavelength = 2
         self._scalingDeCom = np.array(scalingDeCom, dtype=np.float64)
         self._motherWavelength = len(self._scalingDeCom)
         if waveletDeCom is None:
             self._buildOrthonormalSpace()
-        else:  # Haar1.java:62-72 writes its filters out by hand
+        else:  # Haar1.java:62-72 writes its filters out by hand; the BiOrthogonal classes keep four
             self._waveletDeCom = np.array(waveletDeCom, dtype=np.float64)
-            self._scalingReCon = self._scalingDeCom.copy()
-            self._waveletReCon = self._waveletDeCom.copy()
+            self._scalingReCon = (self._scalingDeCom.copy() if scalingReCon is None
+                                  else np.array(scalingReCon, dtype=np.float64))
+            self._waveletReCon = (self._waveletDeCom.copy() if waveletReCon is None
+                                  else np.array(waveletReCon, dtype=np.float64))
 
     def _buildOrthonormalSpace(self):
         """Wavelet.java:104-122"""
@@ -125,6 +128,28 @@ def Legendre3():
     return _legendre("Legendre 3", (-63.0, -35.0, -30.0, -30.0, -35.0, -63.0), 128.0)
 
 
+def Haar1Orthogonal():
+    """haar/Haar1Orthogonal.java:137-161 with the _energyCorrectionFactor of its reverse step
+    (:39, :197-199) folded into the reconstruction filters: .5 * (a s + d w) == a (.5 s) + d (.5 w)
+    exactly in binary floating point, so the device needs no special case."""
+    s = np.array([1.0, 1.0])
+    w = np.array([s[1], -s[0]])
+    return Wavelet("Haar orthogonal", s, w, 0.5 * s, 0.5 * w)
+
+
+def _bior_factory(cls):
+    def make():
+        name, built, arrays = BIOR_TAPS[cls]
+        s_de, w_de = (np.array(a, dtype=np.float64) for a in arrays[:2])
+        if built:  # biorthogonal/BiOrthogonal.java:43-66 (_buildBiOrthonormalSpace)
+            sign = np.where(np.arange(len(s_de)) % 2 == 0, -1.0, 1.0)
+            return Wavelet(name, s_de, w_de, sign * w_de, sign * s_de)
+        return Wavelet(name, s_de, w_de, arrays[2], arrays[3])
+    make.__name__ = cls
+    make.__doc__ = f"the four filters of the reference's biorthogonal/{cls}.java"
+    return make
+
+
 def _literal_factory(cls):
     def make():
         name, taps = LITERAL_TAPS[cls]
@@ -139,7 +164,17 @@ for _cls in LITERAL_TAPS:
     _FACTORIES[_cls] = _literal_factory(_cls)
     globals()[_cls] = _FACTORIES[_cls]
 
+# section 8(f) row 3: four independent filters (generic one-level kernels, or the fused ones when the
+# decomposition / reconstruction pairs happen to be mirrored)
+_FACTORIES["Haar1Orthogonal"] = Haar1Orthogonal
+for _cls in BIOR_TAPS:
+    _FACTORIES[_cls] = _bior_factory(_cls)
+    globals()[_cls] = _FACTORIES[_cls]
+
 WAVELET_CLASSES = tuple(_FACTORIES)
+# the reference's own test loops (WaveletBuilder.java:427-502) include these BiOrthogonal members only
+_BIOR_IN_CREATE2ARR = ("BiOrthogonal11", "BiOrthogonal13", "BiOrthogonal15", "BiOrthogonal31", "BiOrthogonal33",
+                       "BiOrthogonal35", "BiOrthogonal37", "BiOrthogonal39")
 
 
 class WaveletBuilder:
@@ -159,6 +194,8 @@ class WaveletBuilder:
 
     @staticmethod
     def create2arr():
-        """The wavelets the reference's own test loops run over (WaveletBuilder.java:427-502),
-        minus the out-of-scope BiOrthogonal family: Legendre1-3 are excluded there, too."""
-        return [f() for n, f in _FACTORIES.items() if not n.startswith("Legendre")]
+        """The wavelets the reference's own test loops run over (WaveletBuilder.java:427-502): no
+        Legendre, no Haar1Orthogonal, and of the BiOrthogonal family only 1/x and 3/x."""
+        return [f() for n, f in _FACTORIES.items()
+                if not n.startswith("Legendre") and n != "Haar1Orthogonal"
+                and (not n.startswith("BiOrthogonal") or n in _BIOR_IN_CREATE2ARR)]

@@ -27,6 +27,7 @@ class Wavelet(C.Structure):
         ("waveletDeCom", C.c_double * MAX_TAPS),
         ("scalingReCon", C.c_double * MAX_TAPS),
         ("waveletReCon", C.c_double * MAX_TAPS),
+        ("reconFactor", C.c_double),
     ]
 
     def taps(self):
@@ -37,7 +38,7 @@ class Wavelet(C.Structure):
 
 def build(force=False):
     """Compile the oracle with the committed Makefile (gcc, -ffp-contract=off)."""
-    src = [os.path.join(_HERE, f) for f in ("jw_oracle.c", "jw_oracle.h", "jw_taps_literal.inc")]
+    src = [os.path.join(_HERE, f) for f in ("jw_oracle.c", "jw_oracle.h", "jw_taps_literal.inc", "jw_taps_bior.inc")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _SO

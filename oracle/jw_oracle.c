@@ -20,7 +20,7 @@
  * Tap tables
  * ---------------------------------------------------------------------------------------- */
 
-#define JWO_MAX_WAVELETS 64
+#define JWO_MAX_WAVELETS 96
 
 static jwo_wavelet g_wavelets[JWO_MAX_WAVELETS];
 static int g_count = 0;
@@ -47,6 +47,7 @@ static jwo_wavelet* new_wavelet(const char* cls, const char* name, int L) {
   strncpy(w->name, name, sizeof(w->name) - 1);
   w->motherWavelength = L;
   w->transformWavelength = 2;
+  w->reconFactor = 1.;
   return w;
 }
 
@@ -54,6 +55,53 @@ static void add_literal(const char* cls, const char* name, int L, const double* 
   jwo_wavelet* w = new_wavelet(cls, name, L);
   for (int i = 0; i < L; i++) w->scalingDeCom[i] = taps[i];
   build_orthonormal_space(w);
+}
+
+/* transforms/wavelets/biorthogonal/BiOrthogonal.java:43-66 (_buildBiOrthonormalSpace) */
+static void build_biorthonormal_space(jwo_wavelet* w) {
+  int L = w->motherWavelength;
+  for (int i = 0; i < L; i++) {
+    if (i % 2 == 0) {
+      w->scalingReCon[i] = -w->waveletDeCom[i];
+      w->waveletReCon[i] = -w->scalingDeCom[i];
+    } else {
+      w->scalingReCon[i] = w->waveletDeCom[i];
+      w->waveletReCon[i] = w->scalingDeCom[i];
+    }
+  }
+}
+
+/* transforms/wavelets/biorthogonal/BiOrthogonal{11..68}.java: `lit` holds _scalingDeCom, _waveletDeCom
+ * and, unless the constructor builds them, _scalingReCon and _waveletReCon (L literals each) */
+static void add_bior(const char* cls, const char* name, int L, int built, const double* lit) {
+  jwo_wavelet* w = new_wavelet(cls, name, L);
+  for (int i = 0; i < L; i++) {
+    w->scalingDeCom[i] = lit[i];
+    w->waveletDeCom[i] = lit[L + i];
+  }
+  if (built) {
+    build_biorthonormal_space(w);
+  } else {
+    for (int i = 0; i < L; i++) {
+      w->scalingReCon[i] = lit[2 * L + i];
+      w->waveletReCon[i] = lit[3 * L + i];
+    }
+  }
+}
+
+/* transforms/wavelets/haar/Haar1Orthogonal.java:137-161: un-normalised Haar, the reverse step carries
+ * the factor .5 */
+static void add_haar1_orthogonal(void) {
+  jwo_wavelet* w = new_wavelet("Haar1Orthogonal", "Haar orthogonal", 2);
+  w->scalingDeCom[0] = 1.;
+  w->scalingDeCom[1] = 1.;
+  w->waveletDeCom[0] = w->scalingDeCom[1];
+  w->waveletDeCom[1] = -w->scalingDeCom[0];
+  for (int i = 0; i < 2; i++) {
+    w->scalingReCon[i] = w->scalingDeCom[i];
+    w->waveletReCon[i] = w->waveletDeCom[i];
+  }
+  w->reconFactor = .5;
 }
 
 static void add_analytic(void) {
@@ -166,6 +214,14 @@ __attribute__((constructor)) static void init_registry(void) {
   }
 #include "jw_taps_literal.inc"
 #undef JW_LITERAL_WAVELET
+  add_haar1_orthogonal();
+#define JW_BIOR_WAVELET(cls, name, L, built, ...) \
+  {                                               \
+    static const double lit_[] = {__VA_ARGS__};   \
+    add_bior(cls, name, L, built, lit_);          \
+  }
+#include "jw_taps_bior.inc"
+#undef JW_BIOR_WAVELET
 }
 
 int jwo_wavelet_count(void) {
@@ -220,7 +276,8 @@ void jwo_wavelet_forward(const jwo_wavelet* w, const double* arrTime, int n, dou
   }
 }
 
-/* transforms/wavelets/Wavelet.java:277-303 */
+/* transforms/wavelets/Wavelet.java:277-303; identical loops in biorthogonal/BiOrthogonal.java:108-133;
+ * haar/Haar1Orthogonal.java:175-207 multiplies every term by its _energyCorrectionFactor */
 void jwo_wavelet_reverse(const jwo_wavelet* w, const double* arrHilb, int n, double* arrTime) {
   const int L = w->motherWavelength;
   for (int i = 0; i < n; i++) arrTime[i] = 0.;
@@ -229,7 +286,10 @@ void jwo_wavelet_reverse(const jwo_wavelet* w, const double* arrHilb, int n, dou
     for (int j = 0; j < L; j++) {
       int k = (i << 1) + j;
       while (k >= n) k -= n;
-      arrTime[k] += (arrHilb[i] * w->scalingReCon[j]) + (arrHilb[i + h] * w->waveletReCon[j]);
+      if (w->reconFactor == 1.)
+        arrTime[k] += (arrHilb[i] * w->scalingReCon[j]) + (arrHilb[i + h] * w->waveletReCon[j]);
+      else
+        arrTime[k] += w->reconFactor * ((arrHilb[i] * w->scalingReCon[j]) + (arrHilb[i + h] * w->waveletReCon[j]));
     }
   }
 }

@@ -41,9 +41,13 @@ typedef struct jwo_wavelet {
   double waveletDeCom[JWO_MAX_TAPS];
   double scalingReCon[JWO_MAX_TAPS];
   double waveletReCon[JWO_MAX_TAPS];
+  /* 1.0, except transforms/wavelets/haar/Haar1Orthogonal.java:39 (_energyCorrectionFactor = .5),
+   * which scales every reconstruction term (Haar1Orthogonal.java:197-199) */
+  double reconFactor;
 } jwo_wavelet;
 
-/* Registry of the in-scope families: Haar1, Daubechies2-20, Symlet2-20, Coiflet1-5, Legendre1-3. */
+/* Registry: Haar1, Daubechies2-20, Symlet2-20, Coiflet1-5, Legendre1-3 (the north-star families), then
+ * Haar1Orthogonal and BiOrthogonal 1/1 .. 6/8 (four independent filters). */
 int jwo_wavelet_count(void);
 const jwo_wavelet* jwo_wavelet_at(int idx);
 /* Lookup by Java class name ("Symlet8") or display name ("Symlet 8"); NULL when unknown. */

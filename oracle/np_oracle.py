@@ -65,9 +65,33 @@ def _literal():
     return out
 
 
+def _bior():
+    """transforms/wavelets/biorthogonal/BiOrthogonal{11..68}.java (+ BiOrthogonal.java:43-66 where the
+    constructor builds the reconstruction filters) and haar/Haar1Orthogonal.java:137-161."""
+    txt = open(os.path.join(_HERE, "jw_taps_bior.inc")).read()
+    out = {}
+    for m in re.finditer(r'JW_BIOR_WAVELET\("(\w+)",\s*"([^"]+)",\s*(\d+),\s*(\d),([^)]*)\)', txt):
+        L, built = int(m.group(3)), int(m.group(4))
+        v = np.array([float(t) for t in m.group(5).replace("\n", " ").split(",")])
+        assert len(v) == (2 if built else 4) * L
+        s_de, w_de = v[:L], v[L:2 * L]
+        if built:
+            sign = np.where(np.arange(L) % 2 == 0, -1.0, 1.0)
+            s_re, w_re = sign * w_de, sign * s_de
+        else:
+            s_re, w_re = v[2 * L:3 * L], v[3 * L:]
+        out[m.group(1)] = (s_de, w_de, s_re, w_re)
+    one = np.array([1.0, 1.0])
+    out["Haar1Orthogonal"] = (one, np.array([1.0, -1.0]), one.copy(), np.array([1.0, -1.0]))
+    return out
+
+
 WAVELETS = {}
 WAVELETS.update(_analytic())
 WAVELETS.update(_literal())
+WAVELETS.update(_bior())
+# haar/Haar1Orthogonal.java:39, :197-199: every reconstruction term times _energyCorrectionFactor
+RECON_FACTOR = {"Haar1Orthogonal": 0.5}
 
 
 def wavelet_forward(name, x, n):
@@ -93,6 +117,8 @@ def wavelet_reverse(name, c, n):
     j = np.tile(np.arange(L), h)
     k = (2 * i + j) % n
     vals = (c[i] * s_re[j]) + (c[i + h] * w_re[j])
+    if name in RECON_FACTOR:
+        vals = RECON_FACTOR[name] * vals
     t = np.zeros(n)
     np.add.at(t, k, vals)  # unbuffered, applied in index order == the Java loop order
     return t

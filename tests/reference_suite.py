@@ -14,9 +14,15 @@ from jwave_b200.wavelets import WAVELET_CLASSES
 
 KAT = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_kat.json")))
 
-# WaveletBuilder.create2arr() (WaveletBuilder.java:427-502) minus the out-of-scope BiOrthogonals
-CREATE2ARR = [c for c in WAVELET_CLASSES if not c.startswith("Legendre")]
+# WaveletBuilder.create2arr() (WaveletBuilder.java:427-502): the orthonormal families without Legendre,
+# and BiOrthogonal 1/1, 1/3, 1/5, 3/1 .. 3/9 (the members the reference keeps in its own test loops)
+_NAMES = {WaveletBuilder.create(c).getName(): c for c in WAVELET_CLASSES}
+CREATE2ARR = [_NAMES[w.getName()] for w in WaveletBuilder.create2arr()]
 LEGENDRE = [c for c in WAVELET_CLASSES if c.startswith("Legendre")]
+# four independent filters; the ones outside CREATE2ARR do not
+# reconstruct in the reference either (WaveletBuilder.java:481-492 comments them out)
+FOUR_FILTER = [c for c in WAVELET_CLASSES if c.startswith("BiOrthogonal") or c == "Haar1Orthogonal"]
+ORTHONORMAL = [c for c in WAVELET_CLASSES if c not in FOUR_FILTER]
 
 
 def assert_array(expected, actual, delta):

@@ -90,7 +90,7 @@ def test_1d_parity_all_wavelets(kind, cls):
             close(t.reverse(cf, level), co.transform_1d(okind(kind), co.REVERSE, cls, cf, level), np.abs(cf).max())
 
 
-@pytest.mark.parametrize("cls", CONFIG_WAVELETS)
+@pytest.mark.parametrize("cls", CONFIG_WAVELETS + ["BiOrthogonal68", "BiOrthogonal13"])
 @pytest.mark.parametrize("kind", ["fwt", "wpt"])
 def test_batch_parity(kind, cls):
     """forwardBatch / reverseBatch on ragged batch sizes and the config lengths (2^14, 2^16)."""
@@ -113,7 +113,7 @@ def test_input_is_not_mutated_and_output_is_fresh():
 
 
 @pytest.mark.parametrize("kind", ["fwt", "wpt"])
-@pytest.mark.parametrize("cls", ["Haar1", "Daubechies4", "Daubechies20", "Coiflet5"])
+@pytest.mark.parametrize("cls", ["Haar1", "Daubechies4", "Daubechies20", "Coiflet5", "BiOrthogonal37", "Haar1Orthogonal"])
 def test_2d_parity(kind, cls):
     t = make(kind, cls)
     for rows, cols, lv in ((64, 64, None), (16, 128, (2, 5)), (256, 8, (8, 0)), (1, 32, (0, 5)), (128, 256, None),

@@ -16,7 +16,8 @@ def make(kind, cls):
 
 def test_registry_is_the_in_scope_set():
     names = co.wavelet_names()
-    assert len(names) == 47 and len(set(names)) == 47
+    assert len(names) == 63 and len(set(names)) == 63  # 47 orthonormal + Haar1Orthogonal + 15 BiOrthogonal
+    assert names[:47] == rs.ORTHONORMAL and set(names[47:]) == set(rs.FOUR_FILTER)
     assert {"Haar1", "Daubechies4", "Symlet8", "Daubechies20", "Coiflet5", "Legendre3"} <= set(names)
     for cls, L in (("Haar1", 2), ("Daubechies4", 8), ("Symlet8", 16), ("Coiflet5", 30), ("Daubechies20", 40)):
         assert co.wavelet(cls).contents.motherWavelength == L
@@ -30,7 +31,7 @@ def test_filter_fixtures():
     rs.check_haar_filters()
 
 
-@pytest.mark.parametrize("cls", co.wavelet_names())
+@pytest.mark.parametrize("cls", rs.ORTHONORMAL)
 def test_tap_identities(cls):
     """sum h = sqrt 2 (Legendre: -sqrt 2), g[i] = (-1)^i h[L-1-i], recon == decomp; and
     sum h^2 = 1 plus double-shift orthogonality wherever SURVEY.md F8 says the table has them."""
@@ -47,6 +48,29 @@ def test_tap_identities(cls):
     assert abs((s_de ** 2).sum() - 1.0) < tol
     for k in range(1, L // 2):
         assert abs(np.dot(s_de[2 * k:], s_de[: L - 2 * k])) < tol
+
+
+@pytest.mark.parametrize("cls", rs.FOUR_FILTER)
+def test_four_filter_identities(cls):
+    """biorthogonal/BiOrthogonal.java:43-66 where the constructor builds the reconstruction pair; perfect
+    reconstruction of one level (sum over shifts of analysis x synthesis = identity) exactly for the
+    members the reference keeps in create2arr (WaveletBuilder.java:427-502) and for Haar1Orthogonal."""
+    from jwave_b200._taps_bior import BIOR_TAPS
+    w = co.wavelet(cls).contents
+    s_de, w_de, s_re, w_re = w.taps()
+    L = len(s_de)
+    if cls in BIOR_TAPS and BIOR_TAPS[cls][1]:
+        sign = np.where(np.arange(L) % 2 == 0, -1.0, 1.0)
+        assert np.array_equal(s_re, sign * w_de) and np.array_equal(w_re, sign * s_de)
+    n = 64
+    eye = np.eye(n)
+    back = np.stack([co.transform_1d(co.FWT, co.REVERSE, cls, co.transform_1d(co.FWT, co.FORWARD, cls, e, 1), 1)
+                     for e in eye])
+    err = np.abs(back - eye).max()
+    if cls in rs.CREATE2ARR or cls == "Haar1Orthogonal":
+        assert err < 1e-12
+    else:
+        assert err > 0.1  # as in the reference: these members do not reconstruct
 
 
 @pytest.mark.parametrize("cls", rs.CREATE2ARR)
