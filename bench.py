@@ -56,28 +56,79 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock and clock-event (throttle) reasons sampled DURING the timed region (B200_PROFILING.md):
+    NVML every 5 ms when pynvml is importable, else one nvidia-smi query per 100 ms."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
-    def __init__(self, index):
+    def __init__(self, index, uuid=None):
         self.index = index
-        self.rows = []
+        self.sm, self.mx, self.reasons, self.power = [], [], set(), []
         self._stop = threading.Event()
         self._t = threading.Thread(target=self._run, daemon=True)
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if uuid:
+                for cand in (f"GPU-{uuid}", str(uuid)):
+                    try:
+                        h = pynvml.nvmlDeviceGetHandleByUUID(cand.encode() if isinstance(cand, str) else cand)
+                        break
+                    except Exception:
+                        try:
+                            h = pynvml.nvmlDeviceGetHandleByUUID(cand)
+                            break
+                        except Exception:
+                            h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self._nvml, self._h = pynvml, h
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        n, h = self._nvml, self._h
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)))
+        self.mx.append(float(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)))
+        try:
+            self.power.append(n.nvmlDeviceGetPowerUsage(h) / 1000.0)
+        except Exception:
+            pass
+        try:
+            mask = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        for name, bit in self.BITS:
+            if mask & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        f = [t.strip() for t in out.strip().split(",")]
+        if len(f) >= 7:
+            if f[0].replace(".", "").isdigit():
+                self.sm.append(float(f[0]))
+            if f[1].replace(".", "").isdigit():
+                self.mx.append(float(f[1]))
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(name)
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [t.strip() for t in out.strip().split(",")]
-                if len(f) >= 7:
-                    self.rows.append(f)
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.005 if self._nvml is not None else 0.1)
 
     def start(self):
         self._t.start()
@@ -85,15 +136,14 @@ class ClockSampler:
     def stop(self):
         self._stop.set()
         self._t.join(timeout=10)
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(self.rows), "reasons": sorted(reasons)}
+        out = {"sm_mhz": statistics.median(self.sm) if self.sm else None,
+               "sm_min_mhz": min(self.sm) if self.sm else None,
+               "sm_max_mhz": max(self.mx) if self.mx else None,
+               "samples": len(self.sm), "reasons": sorted(self.reasons),
+               "source": "nvml" if self._nvml is not None else "nvidia-smi"}
+        if self.power:
+            out["power_w_median"] = statistics.median(self.power)
+        return out
 
 
 def oracle_step(co, cls, kind, x, level, threads, pwpt=False):
@@ -266,7 +316,7 @@ def main():
     rt_err = float((back - x).abs().max())  # sanity: the timed work really is a transform pair
 
     # ---- timed region: K steps, device resident ------------------------------------------------
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local, getattr(torch.cuda.get_device_properties(local), "uuid", None)) if rank == 0 else None
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     fwd_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches0 = dev.launch_count()
