@@ -39,8 +39,8 @@ __device__ __forceinline__ void fwd_str_level_tile(const Taps& taps, const doubl
                                                    int gpp, Store store) {
   for (int g = g0; g < groups; g += gpp) {
     double lo[kSR], hi[kSR];
-    if constexpr (TMA0) fwd_run<L, kSR>(taps, [&](int s) { return tma_at(cur, 2 * kSR * g + s, c); }, lo, hi);
-    else fwd_run<L, kSR>(taps, [&](int s) { return sat(cur, 2 * kSR * g + s, c); }, lo, hi);
+    if constexpr (TMA0) fwd_run<L, kSR>(taps, tap_phase<L, false>(), [&](int s) { return tma_at(cur, 2 * kSR * g + s, c); }, lo, hi);
+    else fwd_run<L, kSR>(taps, tap_phase<L, false>(), [&](int s) { return sat(cur, 2 * kSR * g + s, c); }, lo, hi);
     store(g, lo, hi);
   }
 }
@@ -114,8 +114,8 @@ k_fwt_fwd_str(const __grid_constant__ Taps taps, const FwtFwdStrArgs a, const __
       if (h_out >= kSR) {
         for (int g = g0; g < h_out / kSR; g += kGroupsPerPass) {
           double lo[kSR], hi[kSR];
-          if (tma0) fwd_run<L, kSR>(taps, [&](int s) { return tma_at(cur, (2 * kSR * g + s) & mask, c); }, lo, hi);
-          else fwd_run<L, kSR>(taps, [&](int s) { return sat(cur, (2 * kSR * g + s) & mask, c); }, lo, hi);
+          if (tma0) fwd_run<L, kSR>(taps, tap_phase<L, false>(), [&](int s) { return tma_at(cur, (2 * kSR * g + s) & mask, c); }, lo, hi);
+          else fwd_run<L, kSR>(taps, tap_phase<L, false>(), [&](int s) { return sat(cur, (2 * kSR * g + s) & mask, c); }, lo, hi);
 #pragma unroll
           for (int r = 0; r < kSR; ++r) {
             if (!last) sat(nxt, kSR * g + r, c) = lo[r];
@@ -127,11 +127,12 @@ k_fwt_fwd_str(const __grid_constant__ Taps taps, const FwtFwdStrArgs a, const __
         // columns of 2 or 4 samples: one thread per output, true modular indexing (h < L wraps)
         for (int i = g0; i < h_out; i += kGroupsPerPass) {
           double lo = 0.0, hi = 0.0;
+          const int z = tap_phase<L, false>();
 #pragma unroll
           for (int j = 0; j < L; ++j) {
             const double v = sat(cur, (2 * i + j) & mask, c);   // never the TMA buffer: h >= kBoxRows there
-            lo = fma(v, taps.lo[j], lo);
-            hi = fma(v, hi_tap<L>(taps, j), hi);
+            lo = fma(v, lo_tap<L>(taps, j, z), lo);
+            hi = fma(v, hi_tap<L>(taps, j, z), hi);
           }
           if (!last) sat(nxt, i, c) = lo;
           else gA[int64_t(i) * inner] = lo;
@@ -184,7 +185,7 @@ k_fwt_rev_str(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevS
       for (int g = g0; g < groups; g += kGroupsPerPass) {
         const int top = s0 + kSR * g + kSR - 1;
         double t[2 * kSR];
-        rev_run<L, kSR>(taps, [&](int s) { return sat(A, top - s, c); }, [&](int s) { return sat(D, top - s, c); }, t);
+        rev_run<L, kSR>(taps, tap_phase<L, true>(), [&](int s) { return sat(A, top - s, c); }, [&](int s) { return sat(D, top - s, c); }, t);
 #pragma unroll
         for (int e = 0; e < 2 * kSR; ++e) {
           if (k > 1) sat(Y, 2 * kSR * g + e, c) = t[e];
@@ -210,7 +211,7 @@ k_fwt_rev_str(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevS
         for (int g = g0; g < half / kSR; g += kGroupsPerPass) {
           const int top = kSR * g + kSR - 1;
           double t[2 * kSR];
-          rev_run<L, kSR>(taps, [&](int s) { return sat(A, (top - s) & mask, c); },
+          rev_run<L, kSR>(taps, tap_phase<L, true>(), [&](int s) { return sat(A, (top - s) & mask, c); },
                           [&](int s) { return sat(C, half + ((top - s) & mask), c); }, t);
 #pragma unroll
           for (int e = 0; e < 2 * kSR; ++e) {
@@ -221,14 +222,15 @@ k_fwt_rev_str(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevS
       } else {
         for (int p = g0; p < half; p += kGroupsPerPass) {
           double t0v = 0.0, t1v = 0.0;
+          const int z = tap_phase<L, true>();
 #pragma unroll
           for (int q = 0; q < L / 2; ++q) {
             const int i = (p - q) & mask;
             const double av = sat(A, i, c), dv = sat(C, half + i, c);
-            t0v = fma(av, taps.lo[2 * q], t0v);
-            t0v = fma(dv, hi_tap<L>(taps, 2 * q), t0v);
-            t1v = fma(av, taps.lo[2 * q + 1], t1v);
-            t1v = fma(dv, hi_tap<L>(taps, 2 * q + 1), t1v);
+            t0v = fma(av, lo_tap<L>(taps, 2 * q, z), t0v);
+            t0v = fma(dv, hi_tap<L>(taps, 2 * q, z), t0v);
+            t1v = fma(av, lo_tap<L>(taps, 2 * q + 1, z), t1v);
+            t1v = fma(dv, hi_tap<L>(taps, 2 * q + 1, z), t1v);
           }
           if (!last) { sat(Y, 2 * p, c) = t0v; sat(Y, 2 * p + 1, c) = t1v; }
           else { gY[int64_t(2 * p) * inner] = t0v; gY[int64_t(2 * p + 1) * inner] = t1v; }

@@ -28,6 +28,31 @@ __device__ __forceinline__ double hi_tap(const Taps& t, int j) {
   return (j & 1) ? -t.lo[L - 1 - j] : t.lo[L - 1 - j];
 }
 
+// Long filters: 2 x L uniform registers do not exist for L >= 32 (63 per warp), and ptxas, which hoists
+// the loop-invariant tap loads out of the group loop, then parks taps in 40-80 VECTOR registers (157-184
+// registers per thread, 2-3 CTAs per SM).  Indexing the taps with a zero that comes out of an inline
+// `mov` keeps the loads inside the step: ptxas folds the zero only after its loop-invariant code motion
+// has run, and then streams the taps through the uniform registers with LDCU as the window slides
+// (rev<40>: 178 -> 63 registers, rev<30>: 153 -> 40; C4 reverse +13 %, C5 +9..12 %, same-run A/B in
+// profiles/r01_ab_tap_streaming.txt).  A zero derived from the loop counter is NOT equivalent: ptxas
+// then issues per-thread LDC loads and prefetches them into 110-150 registers (no gain).  The
+// forward kernel for L >= 38 is limited to 3 CTAs per SM by its shared memory either way and loses
+// 6 % to the extra LDCU, so it keeps the hoisted taps.  The contiguous-line kernels (66-76 registers for
+// L = 40) gain nothing from it either (same A/B file).
+template <int L, bool REVERSE>
+__device__ __forceinline__ int tap_phase() {
+  int z = 0;
+  if constexpr (L >= 30 && (REVERSE || L <= 36)) asm volatile("mov.u32 %0, 0;" : "=r"(z));
+  return z;
+}
+template <int L>
+__device__ __forceinline__ double lo_tap(const Taps& t, int j, int z) { return t.lo[j + z]; }
+template <int L>
+__device__ __forceinline__ double hi_tap(const Taps& t, int j, int z) {
+  return (j & 1) ? -t.lo[L - 1 - j + z] : t.lo[L - 1 - j + z];
+}
+
+
 struct WaveletRec {
   bool mirror_de, mirror_re;  // the relation above holds for the decomposition / reconstruction pair
   int L;

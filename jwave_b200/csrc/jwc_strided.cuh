@@ -74,7 +74,7 @@ __device__ __forceinline__ void tma_load_box(void* smem_dst, const void* tmap, i
 // forward: outputs i = R g .. R g + R - 1 of one column; x(s) = input sample 2 R g + s,
 // s = 0 .. 2R + L - 3 (Wavelet.java:244-254, j ascending, FMA-contracted)
 template <int L, int R, class X>
-__device__ __forceinline__ void fwd_run(const Taps& taps, X x, double (&lo)[R], double (&hi)[R]) {
+__device__ __forceinline__ void fwd_run(const Taps& taps, int z, X x, double (&lo)[R], double (&hi)[R]) {
 #pragma unroll
   for (int r = 0; r < R; ++r) lo[r] = hi[r] = 0.0;
 #pragma unroll
@@ -84,8 +84,8 @@ __device__ __forceinline__ void fwd_run(const Taps& taps, X x, double (&lo)[R], 
     for (int r = 0; r < R; ++r) {
       const int j = s - 2 * r;
       if (j >= 0 && j < L) {
-        lo[r] = fma(v, taps.lo[j], lo[r]);
-        hi[r] = fma(v, hi_tap<L>(taps, j), hi[r]);
+        lo[r] = fma(v, lo_tap<L>(taps, j, z), lo[r]);
+        hi[r] = fma(v, hi_tap<L>(taps, j, z), hi[r]);
       }
     }
   }
@@ -95,7 +95,7 @@ __device__ __forceinline__ void fwd_run(const Taps& taps, X x, double (&lo)[R], 
 // t[2 pp + r] = sum_q a[p - q] lo[2q + r] + d[p - q] hi[2q + r];  a(s) / d(s) = coefficient at slot
 // RS g + RS - 1 - s, s = 0 .. RS + L/2 - 2 (walking left)
 template <int L, int RS, class A, class D>
-__device__ __forceinline__ void rev_run(const Taps& taps, A a, D d, double (&t)[2 * RS]) {
+__device__ __forceinline__ void rev_run(const Taps& taps, int z, A a, D d, double (&t)[2 * RS]) {
 #pragma unroll
   for (int r = 0; r < 2 * RS; ++r) t[r] = 0.0;
 #pragma unroll
@@ -105,10 +105,10 @@ __device__ __forceinline__ void rev_run(const Taps& taps, A a, D d, double (&t)[
     for (int pp = 0; pp < RS; ++pp) {
       const int q = s - (RS - 1 - pp);
       if (q >= 0 && q < L / 2) {
-        t[2 * pp] = fma(av, taps.lo[2 * q], t[2 * pp]);
-        t[2 * pp] = fma(dv, hi_tap<L>(taps, 2 * q), t[2 * pp]);
-        t[2 * pp + 1] = fma(av, taps.lo[2 * q + 1], t[2 * pp + 1]);
-        t[2 * pp + 1] = fma(dv, hi_tap<L>(taps, 2 * q + 1), t[2 * pp + 1]);
+        t[2 * pp] = fma(av, lo_tap<L>(taps, 2 * q, z), t[2 * pp]);
+        t[2 * pp] = fma(dv, hi_tap<L>(taps, 2 * q, z), t[2 * pp]);
+        t[2 * pp + 1] = fma(av, lo_tap<L>(taps, 2 * q + 1, z), t[2 * pp + 1]);
+        t[2 * pp + 1] = fma(dv, hi_tap<L>(taps, 2 * q + 1, z), t[2 * pp + 1]);
       }
     }
   }
