@@ -118,6 +118,13 @@ int jwc_wpt3d(jwc_ctx* ctx, int wid, int dir, const double* in, double* out, int
  * (transforms/AncientEgyptianDecomposition.java:97-129, :144-183). */
 int jwc_aed1d(jwc_ctx* ctx, int wid, int kind, int dir, const double* in, double* out, int64_t batch, int n);
 
+/* WaveletTransform.decompose(double[]) (transforms/WaveletTransform.java:136-146): row p of the result is
+ * forward(x, p), p = 0 .. log2 n, for each of `batch` signals: out is [batch][log2 n + 1][n].  One upload,
+ * one one-level launch per row (row p + 1 is row p with its packets / its approximation split once more),
+ * one download - instead of log2 n + 1 separate transforms.  recompose(mat, level) is
+ * jwc_fwt1d / jwc_wpt1d(JWC_REVERSE) of row `level`. */
+int jwc_decompose1d(jwc_ctx* ctx, int wid, int kind, const double* in, double* out, int64_t batch, int n);
+
 /* CompressorMagnitude.compress(double[] / double[][] / double[][][]) - the same operation on `count`
  * coefficients of any rank (compressions/CompressorMagnitude.java:52-118, compressions/Compressor.java:
  * 97-110): magnitude = mean |c|, then c -> (|c| >= magnitude * threshold ? c : 0).  *magnitude (may be
@@ -142,6 +149,7 @@ int jwc_wpt3d_dev(jwc_ctx* ctx, int wid, int dir, const double* in, double* out,
                   int lvlP, int lvlQ, int lvlR);
 int jwc_aed1d_dev(jwc_ctx* ctx, int wid, int kind, int dir, const double* in, double* out, int64_t batch,
                   int n);
+int jwc_decompose1d_dev(jwc_ctx* ctx, int wid, int kind, const double* in, double* out, int64_t batch, int n);
 /* device variant: *magnitude_dev (device pointer, may be NULL) receives the mean, no host sync */
 int jwc_compress_magnitude_dev(jwc_ctx* ctx, const double* in, double* out, int64_t count, double threshold,
                                double* magnitude_dev);

@@ -42,6 +42,15 @@ public abstract class CudaWaveletTransform extends WaveletTransform implements A
     return _cuda.transform1D( _kind, _wid, JWaveCuda.REVERSE, arrHilb, 1, arrHilb.length, level, _cls + "#reverse" );
   }
 
+  /** WaveletTransform.java:136-146 in one native call: row p of the result is forward( arrTime, p ). */
+  @Override public double[ ][ ] decompose( double[ ] arrTime ) throws JWaveException {
+    if( !isBinary( arrTime.length ) )
+      throw new JWaveFailure( _cls + "#decompose - given array length is not 2^p | p E N ... = 1, 2, 4, 8, 16, 32, .. " );
+    int rows = calcExponent( arrTime.length ) + 1;
+    double[ ] flat = _cuda.decompose1D( _kind, _wid, arrTime, rows, _cls + "#decompose" );
+    return unflatten( flat, rows, arrTime.length );
+  }
+
   // ---- batched entry point: rows are independent signals of one length ------------------------
   // (not called forward(double[][]): that overload means a 2-D transform, BasicTransform.java:336)
 

@@ -118,6 +118,24 @@ public final class JWaveCuda implements AutoCloseable {
     }
   }
 
+  /** jwc_decompose1d: one signal of length n -> (log2 n + 1) x n, row p = forward(x, p). */
+  private static final MethodHandle DECOMPOSE =
+      fn( "jwc_decompose1d", FunctionDescriptor.of( I, P, I, I, P, P, ValueLayout.JAVA_LONG, I ) );
+
+  public synchronized double[ ] decompose1D( int kind, int wid, double[ ] x, int rows, String where ) throws JWaveException {
+    try( Arena a = Arena.ofConfined( ) ) {
+      MemorySegment in = a.allocateArray( ValueLayout.JAVA_DOUBLE, x );
+      MemorySegment out = a.allocateArray( ValueLayout.JAVA_DOUBLE, (long) rows * x.length );
+      int st = (int) DECOMPOSE.invokeExact( ctx, wid, kind, in, out, 1L, x.length );
+      check( st, where );
+      return out.toArray( ValueLayout.JAVA_DOUBLE );
+    } catch( JWaveException e ) {
+      throw e;
+    } catch( Throwable t ) {
+      throw new JWaveError( where + ": " + t );
+    }
+  }
+
   /** batch x n signals, flattened row-major; returns a fresh array (the input is never modified). */
   public synchronized double[ ] transform1D( int kind, int wid, int dir, double[ ] flat, long batch, int n, int level,
       String where ) throws JWaveException {

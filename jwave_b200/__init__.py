@@ -5,11 +5,11 @@ host-side mirror of the reference's plug-in interface on top of it; see transfor
 from .compressions import Compressor, CompressorMagnitude
 from .exceptions import JWaveError, JWaveException, JWaveFailure
 from .transforms import (AncientEgyptianDecomposition, BasicTransform, CudaContext, CudaFastWaveletTransform,
-                         CudaWaveletPacketTransform, MathToolKit, Transform, WaveletTransform)
+                         CudaWaveletPacketTransform, MathToolKit, Transform, TransformBuilder, WaveletTransform)
 from .wavelets import WAVELET_CLASSES, Wavelet, WaveletBuilder
 
 __all__ = [
     "AncientEgyptianDecomposition", "BasicTransform", "Compressor", "CompressorMagnitude", "CudaContext", "CudaFastWaveletTransform", "CudaWaveletPacketTransform",
-    "JWaveError", "JWaveException", "JWaveFailure", "MathToolKit", "Transform", "WaveletTransform",
+    "JWaveError", "JWaveException", "JWaveFailure", "MathToolKit", "Transform", "TransformBuilder", "WaveletTransform",
     "WAVELET_CLASSES", "Wavelet", "WaveletBuilder",
 ]

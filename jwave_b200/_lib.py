@@ -40,6 +40,8 @@ SIGNATURES = {
     "jwc_wpt3d": (_int, [_vp, _int, _int, _vp, _vp, _int, _int, _int, _int, _int, _int]),
     "jwc_aed1d": (_int, [_vp, _int, _int, _int, _vp, _vp, _i64, _int]),
     "jwc_aed1d_dev": (_int, [_vp, _int, _int, _int, _vp, _vp, _i64, _int]),
+    "jwc_decompose1d": (_int, [_vp, _int, _int, _vp, _vp, _i64, _int]),
+    "jwc_decompose1d_dev": (_int, [_vp, _int, _int, _vp, _vp, _i64, _int]),
     "jwc_compress_magnitude": (_int, [_vp, _vp, _vp, _i64, C.c_double, _dp]),
     "jwc_compress_magnitude_dev": (_int, [_vp, _vp, _vp, _i64, C.c_double, _vp]),
     "jwc_fwt1d_dev": (_int, [_vp, _int, _int, _vp, _vp, _i64, _int, _int]),

@@ -437,6 +437,61 @@ extern "C" int jwc_aed1d_dev(jwc_ctx* ctx, int wid, int kind, int dir, const dou
   return aed_dev(ctx, wid, kind, dir, in, out, batch, n);
 }
 
+// WaveletTransform.decompose (WaveletTransform.java:136-146): out[b][p][.] = forward(in[b], p).  Row p + 1
+// is row p with one more level applied - to its approximation prefix (FWT; the detail tail is copied) or
+// to every one of its 2^p packets (WPT) - so each row costs one one-level launch.
+static int decompose_dev(jwc_ctx* ctx, int wid, int kind, const double* in, double* out, int64_t batch, int n) {
+  int st = check_axis(ctx, n, 0);
+  if (st) return st;
+  if (batch < 0) return fail(ctx, JWC_ERR_ARG, "negative batch");
+  if (batch == 0) return JWC_OK;
+  const int P = exponent(n);
+  const int64_t sig = int64_t(P + 1) * n;  // doubles per signal in `out`
+  if (in < out + batch * sig && out < in + batch * n) return fail(ctx, JWC_ERR_ARG, "in and out overlap");
+  JWC_CUDA(ctx, cudaSetDevice(ctx->device));
+  const WaveletRec& w = ctx->wavelets[wid];
+  JWC_CUDA(ctx, cudaMemcpy2DAsync(out, size_t(sig) * sizeof(double), in, size_t(n) * sizeof(double),
+                                  size_t(n) * sizeof(double), size_t(batch), cudaMemcpyDeviceToDevice, ctx->stream));
+  for (int p = 0; p < P; ++p) {
+    const int h = n >> p;
+    FwdLevelArgs a;
+    a.inner = 1;
+    a.half = h / 2;
+    cudaError_t e = cudaSuccess;
+    if (kind == JWC_FWT) {
+      a.src = out + int64_t(p) * n;            a.src_os = sig;
+      a.dstA = out + int64_t(p + 1) * n;       a.dstA_os = sig;
+      a.dstD = a.dstA + h / 2;                 a.dstD_os = sig;
+      a.outer = batch;
+      e = launch_fwd_level_generic(ctx, w.L, w.de, a);
+      if (e == cudaSuccess && h < n)
+        e = cudaMemcpy2DAsync(out + int64_t(p + 1) * n + h, size_t(sig) * sizeof(double), out + int64_t(p) * n + h,
+                              size_t(sig) * sizeof(double), size_t(n - h) * sizeof(double), size_t(batch),
+                              cudaMemcpyDeviceToDevice, ctx->stream);
+    } else {
+      for (int64_t b = 0; b < batch && e == cudaSuccess; ++b) {  // 2^p packets of width h per signal
+        a.src = out + b * sig + int64_t(p) * n;        a.src_os = h;
+        a.dstA = out + b * sig + int64_t(p + 1) * n;   a.dstA_os = h;
+        a.dstD = a.dstA + h / 2;                       a.dstD_os = h;
+        a.outer = int64_t(1) << p;
+        e = launch_fwd_level_generic(ctx, w.L, w.de, a);
+      }
+    }
+    if (e != cudaSuccess) {
+      ctx->err = std::string("decompose: ") + cudaGetErrorString(e);
+      return JWC_ERR_CUDA;
+    }
+  }
+  return JWC_OK;
+}
+
+extern "C" int jwc_decompose1d_dev(jwc_ctx* ctx, int wid, int kind, const double* in, double* out, int64_t batch,
+                                   int n) {
+  int st = check_common(ctx, wid, kind, JWC_FORWARD, in, out);
+  if (st) return st;
+  return decompose_dev(ctx, wid, kind, in, out, batch, n);
+}
+
 // CompressorMagnitude on device-resident coefficients; the magnitude stays on the device
 static int compress_dev(jwc_ctx* ctx, const double* in, double* out, int64_t count, double threshold,
                         double* magnitude_dev) {
@@ -590,6 +645,33 @@ extern "C" int jwc_aed1d(jwc_ctx* ctx, int wid, int kind, int dir, const double*
   return staged(ctx, in, out, batch, n, [&](const double* di, double* dout, int64_t cnt) {
     return aed_dev(ctx, wid, kind, dir, di, dout, cnt, n);
   });
+}
+
+// host buffers: chunks of whole signals (the output is log2 n + 1 times the input, so the equal-size
+// staging pipeline above does not apply); upload, decompose, download per chunk on the context's stream
+extern "C" int jwc_decompose1d(jwc_ctx* ctx, int wid, int kind, const double* in, double* out, int64_t batch, int n) {
+  int st = check_common(ctx, wid, kind, JWC_FORWARD, in, out);
+  if (st) return st;
+  if ((st = check_axis(ctx, n, 0))) return st;
+  if (batch < 0) return fail(ctx, JWC_ERR_ARG, "negative batch");
+  if (batch == 0) return JWC_OK;
+  JWC_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t sig = int64_t(exponent(n) + 1) * n;
+  int64_t per_chunk = int64_t(ctx->staging_bytes / (size_t(sig) * sizeof(double)));
+  if (per_chunk < 1) per_chunk = 1;
+  if (per_chunk > batch) per_chunk = batch;
+  if ((st = ensure(ctx, ctx->stage_in[0], size_t(per_chunk) * n * sizeof(double)))) return st;
+  if ((st = ensure(ctx, ctx->stage_out[0], size_t(per_chunk) * sig * sizeof(double)))) return st;
+  double* d_in = static_cast<double*>(ctx->stage_in[0].ptr);
+  double* d_out = static_cast<double*>(ctx->stage_out[0].ptr);
+  for (int64_t first = 0; first < batch; first += per_chunk) {
+    const int64_t cnt = batch - first < per_chunk ? batch - first : per_chunk;
+    JWC_CUDA(ctx, cudaMemcpyAsync(d_in, in + first * n, size_t(cnt) * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if ((st = decompose_dev(ctx, wid, kind, d_in, d_out, cnt, n))) return st;
+    JWC_CUDA(ctx, cudaMemcpyAsync(out + first * sig, d_out, size_t(cnt) * sig * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    JWC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return JWC_OK;
 }
 
 static int t2d_host(jwc_ctx* ctx, int wid, int kind, int dir, const double* in, double* out,

@@ -332,6 +332,30 @@ class _CudaWaveletTransform(WaveletTransform):
         level = self._check(coeffs.shape[1], level, "reverseBatch")
         return self._call(self._f1d, "reverseBatch", _lib.REVERSE, coeffs, coeffs.shape[0], coeffs.shape[1], level)
 
+    # -- decompose: every level materialised, one upload / one launch per level / one download ----------
+    def decompose(self, arrTime):
+        """WaveletTransform.java:136-146 - row p is forward(arrTime, p)."""
+        arrTime = _as_f64(arrTime)
+        if arrTime.ndim != 1:
+            raise JWaveFailure(f"{self._CLS}#decompose - expected a 1-D array")
+        return self.decomposeBatch(arrTime[None, :])[0]
+
+    def decomposeBatch(self, signals):
+        """[batch][n] -> [batch][log2 n + 1][n] (new, like forwardBatch)."""
+        signals = _as_f64(signals)
+        if signals.ndim != 2:
+            raise JWaveFailure(f"{self._CLS}#decomposeBatch - expected a [batch][n] array")
+        batch, n = signals.shape
+        self._check(n, None, "decompose")
+        out = np.empty((batch, self.calcExponent(n) + 1, n))
+        with self._ctx.lock:
+            if self._ctx.handle is None:
+                raise JWaveError(f"{self._CLS}#decompose - the CUDA context is closed")
+            st = self._ctx._lib.jwc_decompose1d(self._ctx.handle, self._wid, self._KIND, signals.ctypes.data,
+                                                out.ctypes.data, batch, n)
+            self._ctx.check(st, f"{self._CLS}#decompose")
+        return out
+
     # -- 2-D / 3-D: whole-array passes instead of 16 384 tiny launches ---------------------------
     def _forward2(self, matTime, lvlM, lvlN):
         rows, cols = matTime.shape
@@ -492,3 +516,31 @@ class Transform:
 
     def getBasicTransform(self):
         return self._basicTransform
+
+
+class TransformBuilder:
+    """TransformBuilder.java:40-95 with the GPU classes registered.  There are
+    no CPU transforms in this package, so the reference's own names map to the CUDA subclasses too; the
+    "Cuda ..." names are what a JWave maintainer would add to the switch."""
+    _NAMES = {
+        "Fast Wavelet Transform": "CudaFastWaveletTransform",
+        "Wavelet Packet Transform": "CudaWaveletPacketTransform",
+        "Cuda Fast Wavelet Transform": "CudaFastWaveletTransform",
+        "Cuda Wavelet Packet Transform": "CudaWaveletPacketTransform",
+    }
+
+    @staticmethod
+    def create(transformName, wavelet, context=None):
+        """create(String, Wavelet) / create(String, String) (TransformBuilder.java:40-93)."""
+        from .wavelets import WaveletBuilder
+        if isinstance(wavelet, str):
+            wavelet = WaveletBuilder.create(wavelet)
+        cls = TransformBuilder._NAMES.get(transformName)
+        if cls is None:  # incl. "Discrete Fourier Transform": not on this path
+            raise JWaveFailure("TransformBuilder::create - unknown type of transform for given string!")
+        return Transform(globals()[cls](wavelet, context=context))
+
+    @staticmethod
+    def identify(transform):
+        """TransformBuilder.java:97-110: the name stored in the wrapped BasicTransform."""
+        return transform.getBasicTransform().getName()

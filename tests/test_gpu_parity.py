@@ -232,6 +232,34 @@ def test_ancient_egyptian_decomposition(kind):
             aed.forward(np.ones(12), 2)
 
 
+@pytest.mark.parametrize("kind", ["fwt", "wpt"])
+@pytest.mark.parametrize("cls", ["Haar1", "Daubechies4", "Symlet8", "Daubechies20", "BiOrthogonal35"])
+def test_decompose_matches_forward_at_every_level(kind, cls):
+    """jwc_decompose1d (WaveletTransform.java:136-146): row p == forward(x, p) of the oracle for every p,
+    single signals and batches, lengths down to 2 (h < L wraps); recompose (:166-176) from the oracle's
+    rows; TransformBuilder routes its names to the GPU classes."""
+    t = make(kind, cls)
+    for n in (2, 8, 64, 1024):
+        x = rng_signal(n * 5 + 1, n)
+        p_max = n.bit_length() - 1
+        want = np.stack([co.transform_1d(okind(kind), co.FORWARD, cls, x, p) for p in range(p_max + 1)])
+        got = t.decompose(x)
+        assert got.shape == (p_max + 1, n)
+        close(got, want, np.abs(x).max())
+        for p in (0, p_max // 2, p_max):
+            close(t.recompose(want, p), co.transform_1d(okind(kind), co.REVERSE, cls, want[p], p), np.abs(want[p]).max())
+    xb = rng_signal(77, 5, 256)
+    gb = t.decomposeBatch(xb)
+    assert gb.shape == (5, 9, 256)
+    for b in range(5):
+        for p in (0, 1, 4, 8):
+            close(gb[b, p], co.transform_1d(okind(kind), co.FORWARD, cls, xb[b], p), np.abs(xb).max())
+    name = "Fast Wavelet Transform" if kind == "fwt" else "Wavelet Packet Transform"
+    tb = jw.TransformBuilder.create("Cuda " + name, jw.WaveletBuilder.create(cls).getName())
+    assert jw.TransformBuilder.identify(tb) == name
+    close(tb.forward(xb[0], 3), co.transform_1d(okind(kind), co.FORWARD, cls, xb[0], 3), np.abs(xb).max())
+
+
 def test_compressor_magnitude():
     """CompressorMagnitude (compressions/CompressorMagnitude.java:52-118) on 1-D / 2-D / 3-D coefficient
     arrays against the oracle: same magnitude to rounding, same zero pattern (coefficients sitting

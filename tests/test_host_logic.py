@@ -68,3 +68,12 @@ def test_cuda_transform_fails_loudly_without_gpu():
         pytest.skip("GPU present")
     with pytest.raises(jw.JWaveError):
         jw.CudaFastWaveletTransform(jw.WaveletBuilder.create("Haar"), context=jw.CudaContext(0))
+
+
+def test_transform_builder_rejects_unknown_names():
+    """TransformBuilder.java:62-65: unknown transform names (and the out-of-scope DFT) are a JWaveFailure;
+    checked before any CUDA context is touched."""
+    with pytest.raises(jw.JWaveFailure):
+        jw.TransformBuilder.create("Discrete Fourier Transform", "Haar")
+    with pytest.raises(jw.JWaveFailure):
+        jw.TransformBuilder.create("Fast Wavelet Transform", "no such wavelet")
