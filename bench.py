@@ -243,6 +243,8 @@ def main():
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--batch", type=int, default=0, help="override signals per GPU (debug only)")
+    ap.add_argument("--slab", choices=["peer", "all2all"], default="peer",
+                    help="c5 on N > 1 GPUs: exchanges folded into peer stores (default) or NCCL all-to-all")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -281,8 +283,16 @@ def main():
     shape = {1: (batch, n), 2: (batch, n, n), 3: (n, n, n)}[dims]
     if dims == 3 and world > 1:
         # config 5 proper: ONE volume, slab-decomposed along i, all-to-all for the i pass
-        from jwave_b200.distributed import SlabVolumeTransform, device_axis_fn
-        slab = SlabVolumeTransform(device_axis_fn(dev), kind=K)
+        from jwave_b200.distributed import PeerSlabVolumeTransform, SlabVolumeTransform, device_axis_fn
+        slab_mode = "all-to-all"
+        if args.slab == "peer" and K == _lib.FWT:
+            try:  # exchanges folded into the kernels' stores over peer-mapped slabs
+                slab = PeerSlabVolumeTransform(dev, n, n, n)
+                slab_mode = "peer stores"
+            except Exception as e:  # no symmetric memory / shape not covered: NCCL path
+                print(f"[bench] peer-mapped slabs unavailable ({e}); using the all-to-all path", file=sys.stderr)
+        if slab is None:
+            slab = SlabVolumeTransform(device_axis_fn(dev), kind=K)
         shape = (n // world, n, n)
     x = torch.randn(*shape, dtype=torch.float64, device="cuda", generator=gen)
     coef = torch.empty_like(x)
@@ -290,20 +300,20 @@ def main():
 
     def run(direction, src, dst):
         if slab is not None:
+            out = None if slab_mode == "peer stores" else dst  # the peer path returns its own symmetric buffer
             if direction == _lib.FORWARD:
-                slab.forward(src, n, level, level, level, out=dst)
-            else:
-                slab.reverse(src, n, level, level, level, out=dst)
+                return slab.forward(src, n, level, level, level, out=out)
+            return slab.reverse(src, n, level, level, level, out=out)
         elif dims == 1:
             dev.transform1d(K, direction, src, level, out=dst)
         elif dims == 2:
             dev.transform2d(K, direction, src, level, level, out=dst)
         else:
             dev.transform3d(K, direction, src, level, level, level, out=dst)
+        return dst
 
     def step():
-        run(_lib.FORWARD, x, coef)
-        run(_lib.REVERSE, coef, back)
+        return run(_lib.REVERSE, run(_lib.FORWARD, x, coef), back)
 
     def barrier():
         if world > 1:
@@ -311,7 +321,7 @@ def main():
         torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 3)):
-        step()
+        back = step()
     barrier()
     rt_err = float((back - x).abs().max())  # sanity: the timed work really is a transform pair
 
@@ -327,9 +337,9 @@ def main():
     ev[0].record()
     for i in range(args.steps):
         fwd_ev[i][0].record()
-        run(_lib.FORWARD, x, coef)
+        c = run(_lib.FORWARD, x, coef)
         fwd_ev[i][1].record()
-        run(_lib.REVERSE, coef, back)
+        run(_lib.REVERSE, c, back)
     ev[1].record()
     barrier()
     clocks = sampler.stop() if sampler else None
@@ -434,7 +444,9 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong" if slab is not None else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc + (f"; one volume slab-decomposed over {world} GPUs, 2 all-to-all per direction"
+            "config": {"workload": desc + (f"; one volume slab-decomposed over {world} GPUs, "
+                                           + ("exchanges folded into the axis kernels' peer stores (3 device barriers per direction)"
+                                              if slab_mode == "peer stores" else "2 all-to-all per direction")
                                            if slab is not None else ""), "step": "forward + reverse of the whole batch",
                        "items_per_gpu": batch, "shape": list(shape), "n": n, "level": level, "wavelet": cls, "taps": L,
                        "parallelism": f"signals sharded over {world} GPU(s), no collective",

@@ -159,6 +159,24 @@ int jwc_compress_magnitude_dev(jwc_ctx* ctx, const double* in, double* out, int6
 int jwc_axis_dev(jwc_ctx* ctx, int wid, int kind, int dir, const double* in, double* out,
                  int64_t outer, int n, int64_t inner, int level);
 
+/* jwc_axis_dev whose FINAL output is stored straight into buffers of peer GPUs (mapped with
+ * jwc_ipc_open or any other peer mapping): the exchange that would follow the pass is folded into
+ * the kernel's stores.  FWT only, and only where the fused kernels apply (returns JWC_ERR_ARG
+ * otherwise - callers fall back to jwc_axis_dev + a collective).
+ *   mode 1 - strided axis (inner a multiple of 8): row s of outer block o goes to
+ *            peer[s >> lg_seg] + o * outer_stride + base_off + (s mod 2^lg_seg) * row_stride + column
+ *   mode 2 - contiguous axis (inner == 1), reverse only: line o * 2^lg_hi + j goes to
+ *            peer[j >> lg_seg] + o * outer_stride + base_off + (j mod 2^lg_seg) * row_stride + sample
+ * Strides and offsets are in doubles.  The caller synchronises the GPUs around the call. */
+typedef struct jwc_remote_map {
+  int mode, world;
+  int lg_seg, lg_hi;
+  int64_t outer_stride, row_stride, base_off;
+  void* peer[8];
+} jwc_remote_map;
+int jwc_axis_dev_remote(jwc_ctx* ctx, int wid, int kind, int dir, const double* in, int64_t outer, int n,
+                        int64_t inner, int level, const jwc_remote_map* map);
+
 /* ---- memory helpers for FFI callers ------------------------------------------------------- */
 int jwc_dev_alloc(jwc_ctx* ctx, size_t bytes, void** dptr);
 int jwc_dev_free(jwc_ctx* ctx, void* dptr);
@@ -166,6 +184,13 @@ int jwc_h2d(jwc_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes); /*
 int jwc_d2h(jwc_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes); /* async on the stream */
 int jwc_host_alloc_pinned(jwc_ctx* ctx, size_t bytes, void** hptr);
 int jwc_host_free_pinned(jwc_ctx* ctx, void* hptr);
+/* Peer mapping between the per-GPU processes of one box (CUDA IPC): export a handle for a
+ * jwc_dev_alloc'd buffer, open another rank's handle (peer access is enabled lazily), close it.  The
+ * slab-decomposed volume uses these so the axis kernels can store straight into the peers' slabs. */
+#define JWC_IPC_HANDLE_BYTES 64
+int jwc_ipc_export(jwc_ctx* ctx, void* dptr, unsigned char handle[JWC_IPC_HANDLE_BYTES]);
+int jwc_ipc_open(jwc_ctx* ctx, const unsigned char handle[JWC_IPC_HANDLE_BYTES], void** dptr);
+int jwc_ipc_close(jwc_ctx* ctx, void* dptr);
 /* Upper bound (bytes) for the staging chunk the host-buffer entry points move per step. */
 int jwc_set_staging_bytes(jwc_ctx* ctx, size_t bytes);
 

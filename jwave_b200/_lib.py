@@ -57,8 +57,20 @@ SIGNATURES = {
     "jwc_d2h": (_int, [_vp, _vp, _vp, C.c_size_t]),
     "jwc_host_alloc_pinned": (_int, [_vp, C.c_size_t, C.POINTER(_vp)]),
     "jwc_host_free_pinned": (_int, [_vp, _vp]),
+    "jwc_ipc_export": (_int, [_vp, _vp, C.POINTER(C.c_ubyte)]),
+    "jwc_ipc_open": (_int, [_vp, C.POINTER(C.c_ubyte), C.POINTER(_vp)]),
+    "jwc_ipc_close": (_int, [_vp, _vp]),
     "jwc_set_staging_bytes": (_int, [_vp, C.c_size_t]),
 }
+
+class RemoteMap(C.Structure):
+    """jwc_remote_map (include/jwave_cuda.h)"""
+    _fields_ = [("mode", C.c_int), ("world", C.c_int), ("lg_seg", C.c_int), ("lg_hi", C.c_int),
+                ("outer_stride", C.c_int64), ("row_stride", C.c_int64), ("base_off", C.c_int64),
+                ("peer", C.c_void_p * 8)]
+
+
+SIGNATURES["jwc_axis_dev_remote"] = (_int, [_vp, _int, _int, _int, _vp, _i64, _int, _i64, _int, C.POINTER(RemoteMap)])
 
 _lib = None
 

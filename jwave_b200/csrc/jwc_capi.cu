@@ -298,6 +298,42 @@ extern "C" int jwc_axis_dev(jwc_ctx* ctx, int wid, int kind, int dir, const doub
   return axis_dev(ctx, wid, kind, dir, in, out, outer, n, inner, level);
 }
 
+extern "C" int jwc_axis_dev_remote(jwc_ctx* ctx, int wid, int kind, int dir, const double* in, int64_t outer, int n,
+                                   int64_t inner, int level, const jwc_remote_map* map) {
+  if (!ctx) return JWC_ERR_ARG;
+  if (!map) return fail(ctx, JWC_ERR_ARG, "null remote map");
+  int st = check_common(ctx, wid, kind, dir, in, map->peer[0]);
+  if (st) return st;
+  if ((st = check_axis(ctx, n, level))) return st;
+  if (kind != JWC_FWT || level < 1) return fail(ctx, JWC_ERR_ARG, "remote stores: FWT with level >= 1 only");
+  if (map->world < 1 || map->world > 8 || map->lg_seg < 0 || map->lg_hi < 0)
+    return fail(ctx, JWC_ERR_ARG, "remote map: bad geometry");
+  const int64_t rows = map->mode == 1 ? n : (map->mode == 2 ? (int64_t(1) << map->lg_hi) : -1);
+  if (rows < 0 || ((rows - 1) >> map->lg_seg) >= map->world) return fail(ctx, JWC_ERR_ARG, "remote map: bad geometry");
+  if (map->mode == 1 && (inner < 8 || inner % 8)) return fail(ctx, JWC_ERR_ARG, "remote map mode 1 needs inner % 8 == 0");
+  if (map->mode == 2 && (inner != 1 || dir != JWC_REVERSE || (outer & (rows - 1))))
+    return fail(ctx, JWC_ERR_ARG, "remote map mode 2: contiguous reverse passes over whole outer blocks only");
+  if (outer < 1) return fail(ctx, JWC_ERR_ARG, "negative batch");
+  RemoteMap rm;
+  rm.mode = map->mode; rm.lg_seg = map->lg_seg; rm.lg_hi = map->lg_hi;
+  rm.outer_stride = map->outer_stride; rm.row_stride = map->row_stride; rm.base_off = map->base_off;
+  for (int i = 0; i < map->world; ++i) {
+    if (!map->peer[i] || (reinterpret_cast<uintptr_t>(map->peer[i]) & 31)) return fail(ctx, JWC_ERR_ARG, "remote map: peer pointer");
+    rm.peer[i] = static_cast<double*>(map->peer[i]);
+  }
+  if ((rm.outer_stride | rm.row_stride | rm.base_off) & 3) return fail(ctx, JWC_ERR_ARG, "remote map: strides must keep 32-byte alignment");
+  JWC_CUDA(ctx, cudaSetDevice(ctx->device));
+  ctx->remote = &rm;
+  cudaError_t e = run_axis(ctx, ctx->wavelets[wid], kind, dir, in, rm.peer[0], outer, n, inner, level);
+  ctx->remote = nullptr;
+  if (e == cudaErrorNotSupported) return fail(ctx, JWC_ERR_ARG, "remote stores: shape not covered by the fused kernels");
+  if (e != cudaSuccess) {
+    ctx->err = std::string("axis transform: ") + cudaGetErrorString(e);
+    return JWC_ERR_CUDA;
+  }
+  return JWC_OK;
+}
+
 static int t1d_dev(jwc_ctx* ctx, int wid, int kind, int dir, const double* in, double* out,
                    int64_t batch, int n, int level) {
   int st = check_common(ctx, wid, kind, dir, in, out);
@@ -758,6 +794,30 @@ extern "C" int jwc_host_free_pinned(jwc_ctx* ctx, void* hptr) {
   JWC_CUDA(ctx, cudaFreeHost(hptr));
   return JWC_OK;
 }
+extern "C" int jwc_ipc_export(jwc_ctx* ctx, void* dptr, unsigned char handle[JWC_IPC_HANDLE_BYTES]) {
+  if (!ctx || !dptr || !handle) return JWC_ERR_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == JWC_IPC_HANDLE_BYTES, "CUDA IPC handle size");
+  JWC_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  JWC_CUDA(ctx, cudaIpcGetMemHandle(&h, dptr));
+  memcpy(handle, &h, sizeof(h));
+  return JWC_OK;
+}
+extern "C" int jwc_ipc_open(jwc_ctx* ctx, const unsigned char handle[JWC_IPC_HANDLE_BYTES], void** dptr) {
+  if (!ctx || !dptr || !handle) return JWC_ERR_ARG;
+  JWC_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  JWC_CUDA(ctx, cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return JWC_OK;
+}
+extern "C" int jwc_ipc_close(jwc_ctx* ctx, void* dptr) {
+  if (!ctx || !dptr) return JWC_ERR_ARG;
+  JWC_CUDA(ctx, cudaSetDevice(ctx->device));
+  JWC_CUDA(ctx, cudaIpcCloseMemHandle(dptr));
+  return JWC_OK;
+}
+
 extern "C" int jwc_set_staging_bytes(jwc_ctx* ctx, size_t bytes) {
   if (!ctx || bytes < sizeof(double)) return JWC_ERR_ARG;
   ctx->staging_bytes = bytes;

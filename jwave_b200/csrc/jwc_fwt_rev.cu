@@ -140,7 +140,7 @@ k_fwt_rev(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevArgs 
         if (k > 1) {
           store_group<kRS>(Y, g, t);
         } else {
-          double* y = a.dst + line * a.dst_os + t0 + 2 * kRS * g;
+          double* y = (a.rm.mode ? remote_line(a.rm, line) : a.dst + line * a.dst_os) + t0 + 2 * kRS * g;
 #pragma unroll
           for (int e = 0; e < kRS / 2; ++e) st_global_v4(y + 4 * e, t[4 * e], t[4 * e + 1], t[4 * e + 2], t[4 * e + 3]);
           static_assert(kRS >= 2, "a group stores at least 4 samples");
@@ -184,7 +184,7 @@ k_fwt_rev(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevArgs 
           if (!last) {
             store_group<kRS>(P[(k - 1) & 1] + ln * capP[(k - 1) & 1], g, t);
           } else {
-            double* y = a.dst + (line0 + ln) * a.dst_os + 2 * kRS * g;
+            double* y = (a.rm.mode ? remote_line(a.rm, line0 + ln) : a.dst + (line0 + ln) * a.dst_os) + 2 * kRS * g;
 #pragma unroll
             for (int e = 0; e < kRS / 2; ++e) st_global_v4(y + 4 * e, t[4 * e], t[4 * e + 1], t[4 * e + 2], t[4 * e + 3]);
           static_assert(kRS >= 2, "a group stores at least 4 samples");
@@ -210,7 +210,7 @@ k_fwt_rev(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevArgs 
           if (!last) {
             P[(k - 1) & 1][ln * capP[(k - 1) & 1] + lay(p)] = make_double2(t0v, t1v);
           } else {
-            double* y = a.dst + (line0 + ln) * a.dst_os + 2 * p;
+            double* y = (a.rm.mode ? remote_line(a.rm, line0 + ln) : a.dst + (line0 + ln) * a.dst_os) + 2 * p;
             y[0] = t0v;
             y[1] = t1v;
           }

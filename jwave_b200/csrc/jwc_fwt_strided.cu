@@ -47,7 +47,8 @@ __device__ __forceinline__ void fwd_str_level_tile(const Taps& taps, const doubl
 
 template <int L, bool RESIDENT, bool TMA>
 __global__ void __launch_bounds__(kThreads)
-k_fwt_fwd_str(const __grid_constant__ Taps taps, const FwtFwdStrArgs a, const __grid_constant__ CUtensorMap tmap) {
+k_fwt_fwd_str(const __grid_constant__ Taps taps, const __grid_constant__ FwtFwdStrArgs a,
+              const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(1024) double smem[];
   const int c = threadIdx.x % kC, g0 = threadIdx.x / kC;
   const int kGroupsPerPass = blockDim.x / kC;
@@ -60,6 +61,9 @@ k_fwt_fwd_str(const __grid_constant__ Taps taps, const FwtFwdStrArgs a, const __
   const double* src = a.src + o * a.src_os + cb * kC;
   double* gD = a.dstD + o * a.dstD_os + cb * kC + c;
   double* gA = a.dstA + o * a.dstA_os + cb * kC + c;
+  // output row -> address: local lines, or the peers' slabs (RemoteMap, jwc_internal.cuh)
+  auto pD = [&](int64_t row) { return a.rmD.mode ? remote_row(a.rmD, o, row) + cb * kC + c : gD + row * inner; };
+  auto pA = [&](int64_t row) { return a.rmA.mode ? remote_row(a.rmA, o, row) + cb * kC + c : gA + row * inner; };
   double* cur = smem;
   double* nxt = smem + a.rows0 * kC;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (a.rows0 + a.rows1) * kC);
@@ -89,8 +93,8 @@ k_fwt_fwd_str(const __grid_constant__ Taps taps, const FwtFwdStrArgs a, const __
 #pragma unroll
         for (int r = 0; r < kSR; ++r) {
           if (!last) sat(nxt, kSR * g + r, c) = lo[r];
-          else if (keep) gA[(rowA + kSR * g + r) * inner] = lo[r];
-          if (keep) gD[(rowD + kSR * g + r) * inner] = hi[r];
+          else if (keep) *pA(rowA + kSR * g + r) = lo[r];
+          if (keep) *pD(rowD + kSR * g + r) = hi[r];
         }
       };
       if (TMA && k == 1) fwd_str_level_tile<L, TMA>(taps, cur, groups, c, g0, kGroupsPerPass, store);
@@ -119,8 +123,8 @@ k_fwt_fwd_str(const __grid_constant__ Taps taps, const FwtFwdStrArgs a, const __
 #pragma unroll
           for (int r = 0; r < kSR; ++r) {
             if (!last) sat(nxt, kSR * g + r, c) = lo[r];
-            else gA[int64_t(kSR * g + r) * inner] = lo[r];
-            gD[int64_t(h_out + kSR * g + r) * inner] = hi[r];
+            else *pA(kSR * g + r) = lo[r];
+            *pD(h_out + kSR * g + r) = hi[r];
           }
         }
       } else {
@@ -135,8 +139,8 @@ k_fwt_fwd_str(const __grid_constant__ Taps taps, const FwtFwdStrArgs a, const __
             hi = fma(v, hi_tap<L>(taps, j, z), hi);
           }
           if (!last) sat(nxt, i, c) = lo;
-          else gA[int64_t(i) * inner] = lo;
-          gD[int64_t(h_out + i) * inner] = hi;
+          else *pA(i) = lo;
+          *pD(h_out + i) = hi;
         }
       }
       __syncthreads();
@@ -164,6 +168,7 @@ k_fwt_rev_str(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevS
   const double* lineD = a.srcD + o * a.srcD_os + cb * kC;
   const double* lineA = a.srcA + o * a.srcA_os + cb * kC;
   double* gY = a.dst + o * a.dst_os + cb * kC + c;
+  auto pY = [&](int64_t row) { return a.rm.mode ? remote_row(a.rm, o, row) + cb * kC + c : gY + row * inner; };
 
   if constexpr (!RESIDENT) {
     const int T = a.T, t0 = tile * T;
@@ -189,7 +194,7 @@ k_fwt_rev_str(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevS
 #pragma unroll
         for (int e = 0; e < 2 * kSR; ++e) {
           if (k > 1) sat(Y, 2 * kSR * g + e, c) = t[e];
-          else gY[int64_t(t0 + 2 * kSR * g + e) * inner] = t[e];
+          else *pY(t0 + 2 * kSR * g + e) = t[e];
         }
       }
       __syncthreads();
@@ -216,7 +221,7 @@ k_fwt_rev_str(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevS
 #pragma unroll
           for (int e = 0; e < 2 * kSR; ++e) {
             if (!last) sat(Y, 2 * kSR * g + e, c) = t[e];
-            else gY[int64_t(2 * kSR * g + e) * inner] = t[e];
+            else *pY(2 * kSR * g + e) = t[e];
           }
         }
       } else {
@@ -233,7 +238,7 @@ k_fwt_rev_str(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevS
             t1v = fma(dv, hi_tap<L>(taps, 2 * q + 1, z), t1v);
           }
           if (!last) { sat(Y, 2 * p, c) = t0v; sat(Y, 2 * p + 1, c) = t1v; }
-          else { gY[int64_t(2 * p) * inner] = t0v; gY[int64_t(2 * p + 1) * inner] = t1v; }
+          else { *pY(2 * p) = t0v; *pY(2 * p + 1) = t1v; }
         }
       }
       __syncthreads();

@@ -53,6 +53,27 @@ __device__ __forceinline__ double hi_tap(const Taps& t, int j, int z) {
 }
 
 
+// Where the rows / lines of an axis pass's FINAL output go when they are stored straight into the slabs
+// of peer GPUs (slab-decomposed volume, jwc_axis_dev_remote): the exchange that would follow the pass
+// is folded into its stores.
+//   mode 1 (strided axis, row = sample index s of outer block o):
+//       peer[s >> lg_seg] + o * outer_stride + base_off + (s mod 2^lg_seg) * row_stride + column
+//   mode 2 (contiguous axis, line = o * 2^lg_hi + j):
+//       peer[j >> lg_seg] + o * outer_stride + base_off + (j mod 2^lg_seg) * row_stride + sample
+struct RemoteMap {
+  int mode = 0;
+  int lg_seg = 0, lg_hi = 0;
+  int64_t outer_stride = 0, row_stride = 0, base_off = 0;
+  double* peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+__device__ __forceinline__ double* remote_row(const RemoteMap& r, int64_t o, int64_t s) {
+  return r.peer[s >> r.lg_seg] + o * r.outer_stride + r.base_off + (s & ((int64_t(1) << r.lg_seg) - 1)) * r.row_stride;
+}
+__device__ __forceinline__ double* remote_line(const RemoteMap& r, int64_t line) {
+  const int64_t j = line & ((int64_t(1) << r.lg_hi) - 1), o = line >> r.lg_hi;
+  return r.peer[j >> r.lg_seg] + o * r.outer_stride + r.base_off + (j & ((int64_t(1) << r.lg_seg) - 1)) * r.row_stride;
+}
+
 struct WaveletRec {
   bool mirror_de, mirror_re;  // the relation above holds for the decomposition / reconstruction pair
   int L;
@@ -86,6 +107,7 @@ struct jwc_ctx {
   std::vector<jwc::WaveletRec> wavelets;
   std::string err;
   int64_t launches = 0;
+  const jwc::RemoteMap* remote = nullptr;  // set for the duration of one jwc_axis_dev_remote call
   bool prof_on = false;
   std::vector<jwc::ProfRec> prof;
   jwc::Scratch scratch[4];      // [0],[1]: level ping-pong; [2]: axis ping-pong; [3]: alias guard

@@ -32,6 +32,7 @@ struct FwtRevArgs {
   double* dst; int64_t dst_os;          // a_0 lines (width h0)
   int64_t lines;
   int h0, m, T, G;
+  RemoteMap rm;                         // mode 2: the output lines go to peer slabs
   // filled in by the launcher
   int tiles_per_line, ru8;
   int F[kMaxFuse + 2], g0[kMaxFuse + 1], len[kMaxFuse + 1], offD[kMaxFuse + 1], offA[2];
@@ -46,6 +47,7 @@ struct FwtFwdStrArgs {
   double* dstA; int64_t dstA_os;        // a_m destination
   int64_t outer, inner;
   int h, m, T;
+  RemoteMap rmD, rmA;                         // mode 1: the d_k rows / the a_m rows go to peer slabs
   int tiles_per_line, cblocks, rows0, rows1;  // filled in by the launcher
   int64_t rows_per_o;                         // tensor rows between consecutive `outer` slices (TMA path)
 };
@@ -58,6 +60,7 @@ struct FwtRevStrArgs {
   double* dst; int64_t dst_os;
   int64_t outer, inner;
   int h0, m, T;
+  RemoteMap rm;                               // mode 1: the output rows go to peer slabs
   // filled in by the launcher
   int tiles_per_line, cblocks, ru, rowsC, rowsP[2];
   int F[kMaxFuse + 2], s0[kMaxFuse + 1], len[kMaxFuse + 1], offD[kMaxFuse + 1], offA[2];

@@ -107,6 +107,7 @@ static cudaError_t fwt_forward_strided(jwc_ctx* ctx, const WaveletRec& w, const 
   a.src = in; a.src_os = int64_t(n) * inner;
   a.dstD = out; a.dstD_os = int64_t(n) * inner;
   a.outer = outer; a.inner = inner;
+  if (ctx->remote) a.rmD = *ctx->remote;  // every d_k row is final output
   int h = n, left = level, pass = 0;
   while (left > 0) {
     const bool resident = (h <= cap) || (h < tileT);
@@ -114,6 +115,7 @@ static cudaError_t fwt_forward_strided(jwc_ctx* ctx, const WaveletRec& w, const 
     a.T = resident ? h : tileT;
     a.m = resident ? left : (left < m_tile ? left : m_tile);
     const bool last = (a.m == left);
+    a.rmA = (last && ctx->remote) ? *ctx->remote : RemoteMap();  // a_m is final only in the last pass
     a.dstA = last ? out : S[(pass + 1) & 1];
     a.dstA_os = last ? int64_t(n) * inner : int64_t(h >> a.m) * inner;
     JWC_TRY(launch_fwt_fwd_str(ctx, w.L, w.de, a, resident));
@@ -171,6 +173,7 @@ static cudaError_t fwt_reverse_strided(jwc_ctx* ctx, const WaveletRec& w, const 
     a.T = p.resident ? p.h0 : tileT;
     a.dst = last ? out : S[i & 1];
     a.dst_os = last ? int64_t(n) * inner : int64_t(p.h0) * inner;
+    a.rm = (last && ctx->remote) ? *ctx->remote : RemoteMap();
     JWC_TRY(launch_fwt_rev_str(ctx, w.L, w.re, a, p.resident));
     a.srcA = a.dst; a.srcA_os = a.dst_os;
   }
@@ -182,6 +185,7 @@ static cudaError_t fwt_reverse_strided(jwc_ctx* ctx, const WaveletRec& w, const 
 static cudaError_t fwt_forward(jwc_ctx* ctx, const WaveletRec& w, const double* in, double* out,
                                int64_t outer, int n, int64_t inner, int level) {
   if (inner > 1 && w.mirror_de && strided_ok(ctx, in, out, n, inner)) return fwt_forward_strided(ctx, w, in, out, outer, n, inner, level);
+  if (ctx->remote) return cudaErrorNotSupported;  // peer stores exist in the strided forward kernels only
   if (!w.mirror_de || !fused_ok(ctx, in, out, n, inner)) return fwt_forward_generic(ctx, w, in, out, outer, n, inner, level);
   const int cap = ctx->res_cap;
   struct Pass { int h, T, m; bool resident; };
@@ -258,7 +262,10 @@ static cudaError_t fwt_reverse_generic(jwc_ctx* ctx, const WaveletRec& w, const 
 static cudaError_t fwt_reverse(jwc_ctx* ctx, const WaveletRec& w, const double* in, double* out,
                                int64_t outer, int n, int64_t inner, int level) {
   if (inner > 1 && w.mirror_re && strided_ok(ctx, in, out, n, inner)) return fwt_reverse_strided(ctx, w, in, out, outer, n, inner, level);
-  if (!w.mirror_re || !fused_ok(ctx, in, out, n, inner)) return fwt_reverse_generic(ctx, w, in, out, outer, n, inner, level);
+  if (!w.mirror_re || !fused_ok(ctx, in, out, n, inner)) {
+    if (ctx->remote) return cudaErrorNotSupported;  // the one-level kernels store locally only
+    return fwt_reverse_generic(ctx, w, in, out, outer, n, inner, level);
+  }
   struct Pass { int h0, m; bool resident; };
   Pass passes[32];
   int npass = 0;
@@ -307,6 +314,7 @@ static cudaError_t fwt_reverse(jwc_ctx* ctx, const WaveletRec& w, const double* 
     a.G = p.resident ? resident_lines(p.h0, 140) : 1;  // rev: (h + h/2 + h/4) samples, unpadded
     a.dst = last ? out : S[i & 1];
     a.dst_os = last ? n : p.h0;
+    a.rm = (last && ctx->remote) ? *ctx->remote : RemoteMap();
     JWC_TRY(launch_fwt_rev(ctx, w.L, w.re, a, p.resident));
     a.srcA = a.dst; a.srcA_os = a.dst_os;
   }
@@ -442,6 +450,7 @@ static cudaError_t wpt_reverse(jwc_ctx* ctx, const WaveletRec& w, const double* 
 
 cudaError_t run_axis(jwc_ctx* ctx, const WaveletRec& w, int kind, int dir, const double* in, double* out,
                      int64_t outer, int n, int64_t inner, int level) {
+  if (ctx->remote && (level == 0 || n == 1 || kind != JWC_FWT)) return cudaErrorNotSupported;
   if (level == 0 || n == 1) return copy_through(ctx, in, out, outer * n * inner);
   if (kind == JWC_FWT)
     return dir == JWC_FORWARD ? fwt_forward(ctx, w, in, out, outer, n, inner, level)

@@ -43,6 +43,24 @@ class DeviceTransforms:
         self.ctx.check(st, "jwc_axis_dev")
         return out
 
+    def axis_remote(self, kind, direction, x, outer, n, inner, level, peers, mode, lg_seg, lg_hi=0,
+                    outer_stride=0, row_stride=0, base_off=0):
+        """jwc_axis_dev_remote: the pass's final output is stored straight into the peers' buffers
+        (`peers`: device pointers valid on THIS GPU, one per rank) - see include/jwave_cuda.h."""
+        if x.dtype != torch.float64 or not x.is_cuda or x.device != self.device or not x.is_contiguous():
+            raise JWaveFailure("expected a contiguous float64 tensor on " + str(self.device))
+        if outer * n * inner != x.numel():
+            raise JWaveFailure("outer * n * inner must equal the number of elements")
+        self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        m = _lib.RemoteMap()
+        m.mode, m.world, m.lg_seg, m.lg_hi = mode, len(peers), lg_seg, lg_hi
+        m.outer_stride, m.row_stride, m.base_off = outer_stride, row_stride, base_off
+        for i, ptr in enumerate(peers):
+            m.peer[i] = ptr
+        st = self._L.jwc_axis_dev_remote(self.ctx.handle, self.wid, kind, direction, x.data_ptr(), outer, n, inner,
+                                         level, m)
+        self.ctx.check(st, "jwc_axis_dev_remote")
+
     def transform1d(self, kind, direction, x, level, out=None):
         """x: [batch][n]"""
         x, out = self._prep(x, out)

@@ -105,6 +105,74 @@ class SlabVolumeTransform:
         return slab.numel() * slab.element_size() * (self.world - 1) // max(self.world, 1)
 
 
+class PeerSlabVolumeTransform:
+    """The same slab-decomposed 3-D FWT with the exchanges folded into the kernels: every rank maps the
+    slabs of its peers (torch symmetric memory over NVLink / NVSwitch) and the axis pass that precedes an
+    exchange stores its output rows straight into the peer that owns them (jwc_axis_dev_remote), so there
+    is no all-to-all, no pack and no unpack - three device-side barriers per direction instead.
+
+    forward / reverse return a view of an internal symmetric buffer in the i-slab layout [P/W][Q][R]; it
+    stays valid until the next-but-one call.  FWT only (the WPT has no fused strided kernels), P/W and
+    Q/W powers of two, R a multiple of 8; use SlabVolumeTransform otherwise."""
+
+    def __init__(self, dev, P, Q, R, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.dev, self.group = dev, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        W = self.world
+        self.P, self.Q, self.R = P, Q, R
+        self.p, self.q = P // W, Q // W
+        ok = (P % W == 0 and Q % W == 0 and self.p & (self.p - 1) == 0 and self.q & (self.q - 1) == 0
+              and R % 8 == 0 and 2 <= W <= 8)
+        if not ok:
+            raise ValueError("PeerSlabVolumeTransform: P/W and Q/W must be powers of two, R % 8 == 0, 2 <= W <= 8")
+        name = (group or dist.group.WORLD).group_name
+        device = dev.device
+        self._bufs, self._hdl, self._ptrs = {}, {}, {}
+        for key, numel in (("J", P * self.q * R), ("I0", self.p * Q * R), ("I1", self.p * Q * R)):
+            t = symm.empty(numel, dtype=torch.float64, device=device)
+            h = symm.rendezvous(t, name)
+            self._bufs[key], self._hdl[key] = t, h
+            self._ptrs[key] = [h.get_buffer(r, (numel,), torch.float64).data_ptr() for r in range(W)]
+        self._tmp = torch.empty(self.p * Q * R, dtype=torch.float64, device=device)
+        self._flip = 0
+
+    @staticmethod
+    def _lg(v):
+        return v.bit_length() - 1
+
+    def _run(self, direction, slab, lvlP, lvlQ, lvlR):
+        p, q, P, Q, R, rank = self.p, self.q, self.P, self.Q, self.R, self.rank
+        if tuple(slab.shape) != (p, Q, R):
+            raise ValueError("expected this rank's [P/W][Q][R] slab")
+        dev, J = self.dev, self._bufs["J"]
+        key = "I%d" % self._flip
+        self._flip ^= 1
+        if direction == FORWARD:   # BasicTransform.java:509-566 (F5): k gets lvlQ, j gets lvlP, i gets lvlR
+            dev.axis(FWT, FORWARD, slab, p * Q, R, 1, lvlQ, out=self._tmp.view(p, Q, R))
+            self._hdl["J"].barrier()
+            dev.axis_remote(FWT, FORWARD, self._tmp, p, Q, R, lvlP, self._ptrs["J"], 1, self._lg(q),
+                            outer_stride=q * R, row_stride=R, base_off=rank * p * q * R)
+        else:                      # BasicTransform.java:602-659: columns, then rows, then axis i
+            dev.axis(FWT, REVERSE, slab, p, Q, R, lvlP, out=self._tmp.view(p, Q, R))
+            self._hdl["J"].barrier()
+            dev.axis_remote(FWT, REVERSE, self._tmp, p * Q, R, 1, lvlQ, self._ptrs["J"], 2, self._lg(q),
+                            lg_hi=self._lg(Q), outer_stride=q * R, row_stride=R, base_off=rank * p * q * R)
+        self._hdl["J"].barrier()   # every rank's rows have landed in my j-slab
+        dev.axis_remote(FWT, direction, J, 1, P, q * R, lvlR, self._ptrs[key], 1, self._lg(p),
+                        row_stride=Q * R, base_off=rank * q * R)
+        self._hdl[key].barrier()   # ... and in my i-slab
+        return self._bufs[key].view(p, Q, R)
+
+    def forward(self, slab, P, lvlP, lvlQ, lvlR, out=None):
+        y = self._run(FORWARD, slab, lvlP, lvlQ, lvlR)
+        return y if out is None else out.copy_(y)
+
+    def reverse(self, slab, P, lvlP, lvlQ, lvlR, out=None):
+        y = self._run(REVERSE, slab, lvlP, lvlQ, lvlR)
+        return y if out is None else out.copy_(y)
+
+
 def device_axis_fn(dev):
     """axis_fn backed by libjwave_cuda.so through jwave_b200.device.DeviceTransforms."""
     def fn(kind, direction, x, outer, n, inner, level):

@@ -37,6 +37,15 @@ def _worker(rank, world, port, shape, levels, out_dir):
         r = t.reverse(f, P, *levels)
         np.save(os.path.join(out_dir, f"f{rank}.npy"), f.cpu().numpy())
         np.save(os.path.join(out_dir, f"r{rank}.npy"), r.cpu().numpy())
+        # the same volume with the exchanges folded into the kernels' stores (peer-mapped slabs)
+        from jwave_b200.distributed import PeerSlabVolumeTransform
+        pt = PeerSlabVolumeTransform(dev, *shape)
+        for it in range(2):  # twice: buffer reuse across calls must not race
+            pf = pt.forward(slab, P, *levels)
+            pr = pt.reverse(pf, P, *levels)
+        torch.cuda.synchronize()
+        np.save(os.path.join(out_dir, f"pf{rank}.npy"), pf.cpu().numpy())
+        np.save(os.path.join(out_dir, f"pr{rank}.npy"), pr.cpu().numpy())
     finally:
         dist.destroy_process_group()
 
@@ -46,7 +55,7 @@ def test_slab_volume_transform_on_gpus(tmp_path):
     if world < 2:
         pytest.skip("needs at least 2 GPUs")
     import torch.multiprocessing as mp
-    shape, levels = (64, 32, 64), (5, 6, 6)
+    shape, levels = (64, 32, 64), (5, 6, 6)  # (lvlP, lvlQ, lvlR): Q = 32 gets 5, R = 64 gets 6, P = 64 gets 6
     mp.spawn(_worker, args=(world, _free_port(), shape, levels, str(tmp_path)), nprocs=world, join=True)
     vol = np.random.default_rng(5).standard_normal(shape)
     ref_f = co.transform_3d(co.FWT, co.FORWARD, "Coiflet5", vol, *levels)
@@ -55,3 +64,7 @@ def test_slab_volume_transform_on_gpus(tmp_path):
     got_r = np.concatenate([np.load(tmp_path / f"r{r}.npy") for r in range(world)])
     assert np.abs(got_f - ref_f).max() <= 1e-12 * np.abs(vol).max()
     assert np.abs(got_r - ref_r).max() <= 1e-12 * np.abs(ref_f).max()
+    peer_f = np.concatenate([np.load(tmp_path / f"pf{r}.npy") for r in range(world)])
+    peer_r = np.concatenate([np.load(tmp_path / f"pr{r}.npy") for r in range(world)])
+    assert np.array_equal(peer_f, got_f)  # same kernels, same arithmetic: only the stores differ
+    assert np.array_equal(peer_r, got_r)
