@@ -243,8 +243,9 @@ def main():
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--batch", type=int, default=0, help="override signals per GPU (debug only)")
-    ap.add_argument("--slab", choices=["peer", "all2all"], default="peer",
-                    help="c5 on N > 1 GPUs: exchanges folded into peer stores (default) or NCCL all-to-all")
+    ap.add_argument("--slab", choices=["peer", "copies", "all2all"], default="copies",
+                    help="c5 on N > 1 GPUs: peer-mapped slabs filled by strided device copies (default) or by the "
+                         "axis kernels' own stores (peer), or NCCL all-to-all")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -285,10 +286,10 @@ def main():
         # config 5 proper: ONE volume, slab-decomposed along i, all-to-all for the i pass
         from jwave_b200.distributed import PeerSlabVolumeTransform, SlabVolumeTransform, device_axis_fn
         slab_mode = "all-to-all"
-        if args.slab == "peer" and K == _lib.FWT:
-            try:  # exchanges folded into the kernels' stores over peer-mapped slabs
-                slab = PeerSlabVolumeTransform(dev, n, n, n)
-                slab_mode = "peer stores"
+        if args.slab in ("peer", "copies") and K == _lib.FWT:
+            try:  # peer-mapped slabs: exchanges folded into the kernels' stores, or strided device copies
+                slab = PeerSlabVolumeTransform(dev, n, n, n, exchange="stores" if args.slab == "peer" else "copies")
+                slab_mode = "peer stores" if args.slab == "peer" else "peer copies"
             except Exception as e:  # no symmetric memory / shape not covered: NCCL path
                 print(f"[bench] peer-mapped slabs unavailable ({e}); using the all-to-all path", file=sys.stderr)
         if slab is None:
@@ -300,7 +301,7 @@ def main():
 
     def run(direction, src, dst):
         if slab is not None:
-            out = None if slab_mode == "peer stores" else dst  # the peer path returns its own symmetric buffer
+            out = dst if slab_mode == "all-to-all" else None  # the peer paths return their own symmetric buffer
             if direction == _lib.FORWARD:
                 return slab.forward(src, n, level, level, level, out=out)
             return slab.reverse(src, n, level, level, level, out=out)
@@ -445,8 +446,9 @@ def main():
             "scaling": "strong" if slab is not None else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc + (f"; one volume slab-decomposed over {world} GPUs, "
-                                           + ("exchanges folded into the axis kernels' peer stores (3 device barriers per direction)"
-                                              if slab_mode == "peer stores" else "2 all-to-all per direction")
+                                           + {"peer stores": "exchanges folded into the axis kernels' peer stores",
+                                              "peer copies": "blocks copied straight into the peers' slabs (no pack / unpack / NCCL)",
+                                              "all-to-all": "2 all-to-all per direction"}[slab_mode]
                                            if slab is not None else ""), "step": "forward + reverse of the whole batch",
                        "items_per_gpu": batch, "shape": list(shape), "n": n, "level": level, "wavelet": cls, "taps": L,
                        "parallelism": f"signals sharded over {world} GPU(s), no collective",

@@ -115,8 +115,16 @@ class PeerSlabVolumeTransform:
     stays valid until the next-but-one call.  FWT only (the WPT has no fused strided kernels), P/W and
     Q/W powers of two, R a multiple of 8; use SlabVolumeTransform otherwise."""
 
-    def __init__(self, dev, P, Q, R, group=None):
+    def __init__(self, dev, P, Q, R, group=None, exchange="stores"):
+        """exchange = "stores": the axis kernels store into the peers (fewest passes over the data, but a
+        strided-axis CTA owns 64-byte pieces of each row - fine for 2 peers, slow across 8);
+        "copies": the passes stay local and W - 1 strided device copies per exchange write the blocks
+        straight into the peers' slabs in their final layout (wide rows; still no pack, no unpack, no
+        NCCL)."""
         import torch.distributed._symmetric_memory as symm
+        if exchange not in ("stores", "copies"):
+            raise ValueError("exchange must be 'stores' or 'copies'")
+        self.exchange = exchange
         self.dev, self.group = dev, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         W = self.world
@@ -133,8 +141,11 @@ class PeerSlabVolumeTransform:
             t = symm.empty(numel, dtype=torch.float64, device=device)
             h = symm.rendezvous(t, name)
             self._bufs[key], self._hdl[key] = t, h
-            self._ptrs[key] = [h.get_buffer(r, (numel,), torch.float64).data_ptr() for r in range(W)]
+            self._peer = getattr(self, "_peer", {})
+            self._peer[key] = [h.get_buffer(r, (numel,), torch.float64) for r in range(W)]
+            self._ptrs[key] = [t_.data_ptr() for t_ in self._peer[key]]
         self._tmp = torch.empty(self.p * Q * R, dtype=torch.float64, device=device)
+        self._tmp2 = torch.empty(self.p * Q * R, dtype=torch.float64, device=device) if exchange == "copies" else None
         self._flip = 0
 
     @staticmethod
@@ -148,6 +159,8 @@ class PeerSlabVolumeTransform:
         dev, J = self.dev, self._bufs["J"]
         key = "I%d" % self._flip
         self._flip ^= 1
+        if self.exchange == "copies":
+            return self._run_copies(direction, slab, lvlP, lvlQ, lvlR, key)
         if direction == FORWARD:   # BasicTransform.java:509-566 (F5): k gets lvlQ, j gets lvlP, i gets lvlR
             dev.axis(FWT, FORWARD, slab, p * Q, R, 1, lvlQ, out=self._tmp.view(p, Q, R))
             self._hdl["J"].barrier()
@@ -162,6 +175,31 @@ class PeerSlabVolumeTransform:
         dev.axis_remote(FWT, direction, J, 1, P, q * R, lvlR, self._ptrs[key], 1, self._lg(p),
                         row_stride=Q * R, base_off=rank * q * R)
         self._hdl[key].barrier()   # ... and in my i-slab
+        return self._bufs[key].view(p, Q, R)
+
+    def _run_copies(self, direction, slab, lvlP, lvlQ, lvlR, key):
+        p, q, P, Q, R, rank, W = self.p, self.q, self.P, self.Q, self.R, self.rank, self.world
+        dev, J = self.dev, self._bufs["J"]
+        a, b = self._tmp.view(p, Q, R), self._tmp2.view(p, Q, R)
+        if direction == FORWARD:
+            dev.axis(FWT, FORWARD, slab, p * Q, R, 1, lvlQ, out=a)
+            dev.axis(FWT, FORWARD, a, p, Q, R, lvlP, out=b)
+        else:
+            dev.axis(FWT, REVERSE, slab, p, Q, R, lvlP, out=a)
+            dev.axis(FWT, REVERSE, a, p * Q, R, 1, lvlQ, out=b)
+        self._hdl["J"].barrier()
+        src = b.view(p, W, q, R)
+        for k in range(W):  # start with my own block, then round the ring so the peers are hit evenly
+            d = (rank + k) % W
+            self._peer["J"][d].view(P, q, R)[rank * p:(rank + 1) * p].copy_(src[:, d])
+        self._hdl["J"].barrier()
+        y = self._tmp.view(P, q, R)
+        dev.axis(FWT, direction, J.view(P, q, R), 1, P, q * R, lvlR, out=y)
+        self._hdl[key].barrier()
+        for k in range(W):
+            d = (rank + k) % W
+            self._peer[key][d].view(p, W, q, R)[:, rank].copy_(y.view(W, p, q, R)[d])
+        self._hdl[key].barrier()
         return self._bufs[key].view(p, Q, R)
 
     def forward(self, slab, P, lvlP, lvlQ, lvlR, out=None):

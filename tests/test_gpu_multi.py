@@ -46,6 +46,13 @@ def _worker(rank, world, port, shape, levels, out_dir):
         torch.cuda.synchronize()
         np.save(os.path.join(out_dir, f"pf{rank}.npy"), pf.cpu().numpy())
         np.save(os.path.join(out_dir, f"pr{rank}.npy"), pr.cpu().numpy())
+        ct = PeerSlabVolumeTransform(dev, *shape, exchange="copies")
+        for it in range(2):
+            cf = ct.forward(slab, P, *levels)
+            cr = ct.reverse(cf, P, *levels)
+        torch.cuda.synchronize()
+        np.save(os.path.join(out_dir, f"cf{rank}.npy"), cf.cpu().numpy())
+        np.save(os.path.join(out_dir, f"cr{rank}.npy"), cr.cpu().numpy())
     finally:
         dist.destroy_process_group()
 
@@ -68,3 +75,5 @@ def test_slab_volume_transform_on_gpus(tmp_path):
     peer_r = np.concatenate([np.load(tmp_path / f"pr{r}.npy") for r in range(world)])
     assert np.array_equal(peer_f, got_f)  # same kernels, same arithmetic: only the stores differ
     assert np.array_equal(peer_r, got_r)
+    for tag, want in (("cf", got_f), ("cr", got_r)):  # peer-mapped slabs filled by strided device copies
+        assert np.array_equal(np.concatenate([np.load(tmp_path / f"{tag}{r}.npy") for r in range(world)]), want)
