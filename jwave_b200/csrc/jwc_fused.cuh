@@ -6,7 +6,7 @@
 
 namespace jwc {
 
-constexpr int kThreads = 256;  // CTA size of every fused kernel
+constexpr int kThreads = 256;  // upper bound of the CTA size of the strided kernels (launch bound)
 constexpr int kR = 4;          // consecutive outputs (per filter) one thread produces per step
 
 // Shared-memory layout of a line segment: interleaved samples as double2 (x[2k], x[2k+1]), one
@@ -20,9 +20,6 @@ __host__ __device__ constexpr int pad2_size(int n2) { return n2 + (n2 >> 2) + 1;
 // scalar view of a padded double2 line
 __device__ __forceinline__ double sm_scalar(const double2* buf, int i) {
   return reinterpret_cast<const double*>(buf)[2 * pad2(i >> 1) + (i & 1)];
-}
-__device__ __forceinline__ void sm_scalar_store(double2* buf, int i, double v) {
-  reinterpret_cast<double*>(buf)[2 * pad2(i >> 1) + (i & 1)] = v;
 }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
@@ -45,12 +42,9 @@ __device__ __forceinline__ void cp_async_wait_pending(int pending) {
   }
 }
 
-// 256-bit global store / load of 4 consecutive doubles (32-byte aligned): STG.E.ENL2.256 on sm_100a.
+// 256-bit global store of 4 consecutive doubles (32-byte aligned): STG.E.ENL2.256 on sm_100a.
 __device__ __forceinline__ void st_global_v4(double* p, double a, double b, double c, double d) {
   asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
-}
-__device__ __forceinline__ void ld_global_v4(const double* p, double& a, double& b, double& c, double& d) {
-  asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
 }
 
 // Forward step for R consecutive output pairs i = R g' .. R g' + R - 1: `win(q)` returns double2
@@ -112,30 +106,6 @@ __device__ __forceinline__ void fwd_step4(const Taps& taps, Win win, double (&lo
         hi[r] = fma(v.x, hi_tap<L>(taps, 2 * jj), hi[r]);
         lo[r] = fma(v.y, taps.lo[2 * jj + 1], lo[r]);
         hi[r] = fma(v.y, hi_tap<L>(taps, 2 * jj + 1), hi[r]);
-      }
-    }
-  }
-}
-
-// Reverse step (gather form of Wavelet.java:288-299) for 4 consecutive coefficient slots
-// p = 4g .. 4g+3, i.e. 8 consecutive time samples t[8g .. 8g+7]:
-//   t[2p+r] = sum_q a[p-q] * lo[2q+r] + d[p-q] * hi[2q+r],   q = 0 .. L/2-1
-// `ca(s)` / `cd(s)` return a[4g + 3 - s] / d[4g + 3 - s] for s = 0 .. L/2 + 2 (walking left).
-template <int L, class Ca, class Cd>
-__device__ __forceinline__ void rev_step4(const Taps& taps, Ca ca, Cd cd, double (&t)[2 * kR]) {
-#pragma unroll
-  for (int r = 0; r < 2 * kR; ++r) t[r] = 0.0;
-#pragma unroll
-  for (int s = 0; s < L / 2 + kR - 1; ++s) {
-    const double av = ca(s), dv = cd(s);
-#pragma unroll
-    for (int pp = 0; pp < kR; ++pp) {
-      const int q = s - (kR - 1 - pp);  // a[4g+3-s] = a[(4g+pp) - q]
-      if (q >= 0 && q < L / 2) {
-        t[2 * pp] = fma(av, taps.lo[2 * q], t[2 * pp]);
-        t[2 * pp] = fma(dv, hi_tap<L>(taps, 2 * q), t[2 * pp]);
-        t[2 * pp + 1] = fma(av, taps.lo[2 * q + 1], t[2 * pp + 1]);
-        t[2 * pp + 1] = fma(dv, hi_tap<L>(taps, 2 * q + 1), t[2 * pp + 1]);
       }
     }
   }
