@@ -113,7 +113,7 @@ struct jwc_ctx {
   jwc::Scratch scratch[4];      // [0],[1]: level ping-pong; [2]: axis ping-pong; [3]: alias guard
   jwc::Scratch stage_in[2], stage_out[2];
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
-  size_t staging_bytes = size_t(256) << 20;
+  size_t staging_bytes = size_t(64) << 20;  // pipeline ramp = 2 chunks: 64 MiB keeps it below 1 % of an 8 GiB batch
   bool force_generic = false;   // JWC_FORCE_GENERIC=1: only the one-level reference kernels
   // launch-shape tunables (JWC_TUNE="fwd_tile=2048,fwd_m=5,rev_tile=4096,rev_m=5,res_cap=4096")
   int fwd_tile = 2048, fwd_m = 4 /* cap on the halo rule */, fwd_r = 4, rev_tile = 4096, rev_m = 4, rev_rs = 4, fwd_threads = 128, rev_threads = 128, res_cap = 256, res_threads = 128, wpt_tile = 2048, wpt_m = 3, wpt_threads = 160, wpt_rs = 8, wpt_r = 8, wpt_inplace = 1;
