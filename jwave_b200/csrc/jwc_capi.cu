@@ -109,6 +109,7 @@ extern "C" int jwc_create(jwc_ctx** out, int device) {
     get("str_tma", &ctx->str_tma);
     get("wpt_threads", &ctx->wpt_threads);
     get("wpt_inplace", &ctx->wpt_inplace);
+    get("rev_tail", &ctx->rev_tail);
   }
   *out = ctx;
   return JWC_OK;

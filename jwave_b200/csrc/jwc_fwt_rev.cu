@@ -56,6 +56,9 @@ __device__ __forceinline__ void store_group(double2* Y, int g, const double (&t)
 // `a2(w)` / `d2(w)` return double2 number (RS/2 g' + RS/2 - 1 - w) of the a / d arrays, w = 0 .. L/4 + RS/2 - 1.
 template <int L, int RS, class A2, class D2>
 __device__ __forceinline__ void rev_step(const Taps& taps, A2 a2, D2 d2, double (&t)[2 * RS]) {
+  // long filters: keep the tap loads inside the step (tap_phase, jwc_internal.cuh) - with the main and the
+  // tail step in one kernel ptxas otherwise hoists the taps into 100+ vector registers (L = 40: 168)
+  const int z = tap_phase<L, true>();
 #pragma unroll
   for (int r = 0; r < 2 * RS; ++r) t[r] = 0.0;
   constexpr int W = (L / 2) / 2 + RS / 2;
@@ -77,20 +80,24 @@ __device__ __forceinline__ void rev_step(const Taps& taps, A2 a2, D2 d2, double 
       const int qy = pp - (RS - 1) + 2 * w;  // .y is slot RS g' + RS - 1 - 2w
       const int qx = qy + 1;                 // .x is the slot before it
       if (qy >= 0 && qy < L / 2) {
-        t[2 * pp] = fma(av.y, taps.lo[2 * qy], t[2 * pp]);
-        t[2 * pp] = fma(dv.y, hi_tap<L>(taps, 2 * qy), t[2 * pp]);
-        t[2 * pp + 1] = fma(av.y, taps.lo[2 * qy + 1], t[2 * pp + 1]);
-        t[2 * pp + 1] = fma(dv.y, hi_tap<L>(taps, 2 * qy + 1), t[2 * pp + 1]);
+        t[2 * pp] = fma(av.y, lo_tap<L>(taps, 2 * qy, z), t[2 * pp]);
+        t[2 * pp] = fma(dv.y, hi_tap<L>(taps, 2 * qy, z), t[2 * pp]);
+        t[2 * pp + 1] = fma(av.y, lo_tap<L>(taps, 2 * qy + 1, z), t[2 * pp + 1]);
+        t[2 * pp + 1] = fma(dv.y, hi_tap<L>(taps, 2 * qy + 1, z), t[2 * pp + 1]);
       }
       if (qx >= 0 && qx < L / 2) {
-        t[2 * pp] = fma(av.x, taps.lo[2 * qx], t[2 * pp]);
-        t[2 * pp] = fma(dv.x, hi_tap<L>(taps, 2 * qx), t[2 * pp]);
-        t[2 * pp + 1] = fma(av.x, taps.lo[2 * qx + 1], t[2 * pp + 1]);
-        t[2 * pp + 1] = fma(dv.x, hi_tap<L>(taps, 2 * qx + 1), t[2 * pp + 1]);
+        t[2 * pp] = fma(av.x, lo_tap<L>(taps, 2 * qx, z), t[2 * pp]);
+        t[2 * pp] = fma(dv.x, hi_tap<L>(taps, 2 * qx, z), t[2 * pp]);
+        t[2 * pp + 1] = fma(av.x, lo_tap<L>(taps, 2 * qx + 1, z), t[2 * pp + 1]);
+        t[2 * pp + 1] = fma(dv.x, hi_tap<L>(taps, 2 * qx + 1, z), t[2 * pp + 1]);
       }
     }
   }
 }
+
+// Longest filter that gets a tail warp: with both steps in one kernel body ptxas hoists the taps of
+// longer filters out of the level loop into vector registers (L = 40: 66 -> 132 registers).
+constexpr int kTailMaxL = 24;
 
 template <int L, bool RESIDENT, int kRS>
 __global__ void __launch_bounds__(384)
@@ -133,17 +140,34 @@ k_fwt_rev(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevArgs 
       double2* Y = smem2 + a.offA[(k - 1) & 1];
       const int groups = ((T >> k) + a.F[k]) / kRS;
       const int g0 = a.g0[k];
-      for (int g = tid; g < groups; g += nthr) {
-        double t[2 * kRS];
-        const int c = 4 * g0 + (kRS / 2) * g + kRS / 2 - 1;
-        rev_step<L, kRS>(taps, [&](int w) { return A[lay(c - w)]; }, [&](int w) { return D[lay(c - w)]; }, t);
-        if (k > 1) {
-          store_group<kRS>(Y, g, t);
-        } else {
-          double* y = (a.rm.mode ? remote_line(a.rm, line) : a.dst + line * a.dst_os) + t0 + 2 * kRS * g;
+      // With a tail warp (a.tail) the F_k slots of left extension the levels below need - the first
+      // F_k / kRS groups - are its job, two slots per lane; the main warps then run exactly (T >> k) / kRS
+      // groups, a power of two, instead of one more partly filled kRS-wide step per level.
+      const int nmain = nthr - 32 * a.tail;
+      const int gl = a.tail ? a.F[k] / kRS : 0;
+      if (tid < nmain) {
+        for (int g = gl + tid; g < groups; g += nmain) {
+          double t[2 * kRS];
+          const int c = 4 * g0 + (kRS / 2) * g + kRS / 2 - 1;
+          rev_step<L, kRS>(taps, [&](int w) { return A[lay(c - w)]; }, [&](int w) { return D[lay(c - w)]; }, t);
+          if (k > 1) {
+            store_group<kRS>(Y, g, t);
+          } else {
+            double* y = (a.rm.mode ? remote_line(a.rm, line) : a.dst + line * a.dst_os) + t0 + 2 * kRS * g;
 #pragma unroll
-          for (int e = 0; e < kRS / 2; ++e) st_global_v4(y + 4 * e, t[4 * e], t[4 * e + 1], t[4 * e + 2], t[4 * e + 3]);
-          static_assert(kRS >= 2, "a group stores at least 4 samples");
+            for (int e = 0; e < kRS / 2; ++e) st_global_v4(y + 4 * e, t[4 * e], t[4 * e + 1], t[4 * e + 2], t[4 * e + 3]);
+            static_assert(kRS >= 2, "a group stores at least 4 samples");
+          }
+        }
+      } else {
+        // F_k < L <= 40, so the F_k / 2 steps fit the warp's lanes: no loop (a loop here makes ptxas hoist the
+        // taps of long filters out of both loops into vector registers).  F_1 == 0: never at the output level.
+        const int g2 = tid - nmain;
+        if constexpr (L <= kTailMaxL) if (g2 < a.F[k] / 2) {
+          double t4[4];
+          const int c = 4 * g0 + g2;
+          rev_step<L, 2>(taps, [&](int w) { return A[lay(c - w)]; }, [&](int w) { return D[lay(c - w)]; }, t4);
+          store_group<2>(Y, g2, t4);
         }
       }
     }
@@ -269,7 +293,8 @@ static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, FwtRevArgs a, bool r
     if (e != cudaSuccess) return e;
   }
   prof_begin(ctx, resident ? "k_fwt_rev:resident" : "k_fwt_rev:tile", double(a.lines) * a.h0, a.m);
-  kern<<<grid, resident ? ctx->res_threads : ctx->rev_threads, smem, ctx->stream>>>(taps, a);
+  a.tail = (!resident && ctx->rev_tail && L <= kTailMaxL) ? 1 : 0;
+  kern<<<grid, resident ? ctx->res_threads : ctx->rev_threads + 32 * a.tail, smem, ctx->stream>>>(taps, a);
   prof_end(ctx);
   ctx->launches++;
   return cudaGetLastError();

@@ -34,7 +34,7 @@ struct FwtRevArgs {
   int h0, m, T, G;
   RemoteMap rm;                         // mode 2: the output lines go to peer slabs
   // filled in by the launcher
-  int tiles_per_line, ru8;
+  int tiles_per_line, ru8, tail;
   int F[kMaxFuse + 2], g0[kMaxFuse + 1], len[kMaxFuse + 1], offD[kMaxFuse + 1], offA[2];
   int capC, capP[2];
 };
