@@ -110,6 +110,7 @@ extern "C" int jwc_create(jwc_ctx** out, int device) {
     get("wpt_threads", &ctx->wpt_threads);
     get("wpt_inplace", &ctx->wpt_inplace);
     get("rev_tail", &ctx->rev_tail);
+    get("fwd_tail", &ctx->fwd_tail);
   }
   *out = ctx;
   return JWC_OK;

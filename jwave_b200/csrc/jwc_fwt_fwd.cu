@@ -42,11 +42,24 @@ k_fwt_fwd(const __grid_constant__ Taps taps, const FwtFwdArgs a) {
     for (int k = 1; k <= m; ++k) {
       const int n_det = T >> k;                                   // details this tile owns
       const int n_out = n_det + ((1 << (m - k)) - 1) * (L - 2);   // approximations incl. halo
-      const int groups = (n_out + R - 1) / R;
+      // With a tail warp (a.tail, L <= kTailMaxL) the halo approximations are its job, two per lane and
+      // low pass only; the main warps then run exactly n_det / R groups, a power of two.
+      const int nmain = nthr - 32 * a.tail;
+      const int groups = a.tail ? n_det / R : (n_out + R - 1) / R;
       const bool last = (k == m);
       double* dD = outD + (h >> k) + tile * n_det;
       double* dA = a.dstA + line * a.dstA_os + tile * n_det;      // used when last
-      for (int g = tid; g < groups; g += nthr) {
+      if constexpr (L <= kTailMaxL) {
+        if (tid >= nmain) {  // only with a.tail; nothing to do at the last level (no halo)
+          for (int j = tid - nmain; j < (n_out - n_det) / 2; j += 32) {
+            const int o = n_det + 2 * j;  // first of the two outputs == first double2 of their window
+            double lo2[2], hi2[2];
+            fwd_stepR<L, 2>(taps, [&](int q) { return cur[pad2(o + q)]; }, lo2, hi2);
+            nxt[pad2(o >> 1)] = make_double2(lo2[0], lo2[1]);
+          }
+        }
+      }
+      for (int g = tid; g < groups && tid < nmain; g += nmain) {
         double lo[R], hi[R];
         if constexpr (R == 4) {
           const double2* w = cur + pad2(R * g);   // pad2(4g + q) == 5g + q + (q >> 2)
@@ -161,7 +174,8 @@ static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, FwtFwdArgs a, bool r
     if (e != cudaSuccess) return e;
   }
   prof_begin(ctx, resident ? "k_fwt_fwd:resident" : "k_fwt_fwd:tile", double(a.lines) * a.h, a.m);
-  kern<<<grid, resident ? ctx->res_threads : ctx->fwd_threads, smem, ctx->stream>>>(taps, a);
+  a.tail = (!resident && ctx->fwd_tail && L <= kTailMaxL) ? 1 : 0;
+  kern<<<grid, resident ? ctx->res_threads : ctx->fwd_threads + 32 * a.tail, smem, ctx->stream>>>(taps, a);
   prof_end(ctx);
   ctx->launches++;
   return cudaGetLastError();

@@ -95,10 +95,6 @@ __device__ __forceinline__ void rev_step(const Taps& taps, A2 a2, D2 d2, double 
   }
 }
 
-// Longest filter that gets a tail warp: with both steps in one kernel body ptxas hoists the taps of
-// longer filters out of the level loop into vector registers (L = 40: 66 -> 132 registers).
-constexpr int kTailMaxL = 24;
-
 template <int L, bool RESIDENT, int kRS>
 __global__ void __launch_bounds__(384)
 k_fwt_rev(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevArgs a) {

@@ -19,8 +19,11 @@ struct FwtFwdArgs {
   int m;                                // levels fused in this launch
   int T;                                // tile length (tile mode)
   int G;                                // lines per CTA (resident mode)
-  int tiles_per_line, cap0, cap1;       // filled in by the launcher
+  int tiles_per_line, cap0, cap1, tail; // filled in by the launcher
 };
+// Longest filter whose FWT tile kernels get a tail warp: with both steps in one kernel body ptxas hoists
+// the taps of longer filters out of the level loop into vector registers (reverse L = 40: 66 -> 132).
+constexpr int kTailMaxL = 24;
 int fwt_tile_levels(int L, int T);
 cudaError_t launch_fwt_fwd(jwc_ctx* ctx, int L, const Taps& taps, const FwtFwdArgs& a, bool resident);
 
