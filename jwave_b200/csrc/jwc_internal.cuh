@@ -116,7 +116,7 @@ struct jwc_ctx {
   size_t staging_bytes = size_t(64) << 20;  // pipeline ramp = 2 chunks: 64 MiB keeps it below 1 % of an 8 GiB batch
   bool force_generic = false;   // JWC_FORCE_GENERIC=1: only the one-level reference kernels
   // launch-shape tunables (JWC_TUNE="fwd_tile=2048,fwd_m=5,rev_tile=4096,rev_m=5,res_cap=4096")
-  int fwd_tile = 2048, fwd_m = 4 /* cap on the halo rule */, fwd_r = 4, rev_tile = 4096, rev_m = 4, rev_rs = 4, fwd_threads = 128, rev_threads = 128, res_cap = 256, res_threads = 128, wpt_tile = 2048, wpt_m = 3, wpt_threads = 160, wpt_rs = 8, wpt_r = 8, wpt_inplace = 1, rev_tail = 1, fwd_tail = 1;
+  int fwd_tile = 2048, fwd_m = 4 /* cap on the halo rule */, fwd_r = 4, rev_tile = 4096, rev_m = 3, rev_rs = 4, fwd_threads = 128, rev_threads = 128, res_cap = 256, res_threads = 128, wpt_tile = 2048, wpt_m = 3, wpt_threads = 160, wpt_rs = 8, wpt_r = 8, wpt_inplace = 1, rev_tail = 1, fwd_tail = 1;
   int str_tile = 512, str_rev_tile = 512, str_rev_m = 5, str_cap = 512, str_threads = 128, str_rev_threads = 128, str_tma = 1;  // strided-axis kernels
 };
 
