@@ -16,6 +16,23 @@
 
 namespace jwc {
 
+// Tile-mode layout.  Short and medium filters (L <= kXorMaxL): unpadded, double2 k at k ^ ((k >> 3) & 3) -
+// conflict-free for the window loads (lanes 4 slots apart), the a_k stores (2 slots apart) and the
+// cp.async staging (consecutive slots), where the padded layout is 2-way conflicted in the last two
+// (tests/test_smem_layouts.py), and 20 % smaller.  The XOR costs two integer instructions per window load,
+// which the FP64-bound long filters cannot spare: they keep pad2 (compile-time offsets from one base).
+#ifndef JWC_FWD_XOR
+#define JWC_FWD_XOR 1
+#endif
+constexpr int kXorMaxL = JWC_FWD_XOR ? 24 : 0;
+template <int L> __device__ __forceinline__ int fl(int k2) {
+  if constexpr (L <= kXorMaxL) return k2 ^ ((k2 >> 3) & 3);
+  else return pad2(k2);
+}
+template <int L> static constexpr int fl_size(int n2) {
+  return L <= kXorMaxL ? ((n2 + 3) & ~3) : pad2_size(n2);
+}
+
 template <int L, bool RESIDENT, int R = 4>
 __global__ void __launch_bounds__(384)
 k_fwt_fwd(const __grid_constant__ Taps taps, const FwtFwdArgs a) {
@@ -34,7 +51,7 @@ k_fwt_fwd(const __grid_constant__ Taps taps, const FwtFwdArgs a) {
     const double* src = a.src + line * a.src_os;
     const int base = tile * T;
     for (int k2 = tid; k2 < n0 / 2; k2 += nthr)
-      cp_async16(&cur[pad2(k2)], src + ((base + 2 * k2) & (h - 1)));   // periodic wrap of the halo
+      cp_async16(&cur[fl<L>(k2)], src + ((base + 2 * k2) & (h - 1)));   // periodic wrap of the halo
     cp_async_wait_all();
     __syncthreads();
 
@@ -54,27 +71,31 @@ k_fwt_fwd(const __grid_constant__ Taps taps, const FwtFwdArgs a) {
           for (int j = tid - nmain; j < (n_out - n_det) / 2; j += 32) {
             const int o = n_det + 2 * j;  // first of the two outputs == first double2 of their window
             double lo2[2], hi2[2];
-            fwd_stepR<L, 2>(taps, [&](int q) { return cur[pad2(o + q)]; }, lo2, hi2);
-            nxt[pad2(o >> 1)] = make_double2(lo2[0], lo2[1]);
+            fwd_stepR<L, 2>(taps, [&](int q) { return cur[fl<L>(o + q)]; }, lo2, hi2);
+            nxt[fl<L>(o >> 1)] = make_double2(lo2[0], lo2[1]);
           }
         }
       }
       for (int g = tid; g < groups && tid < nmain; g += nmain) {
         double lo[R], hi[R];
         if constexpr (R == 4) {
-          const double2* w = cur + pad2(R * g);   // pad2(4g + q) == 5g + q + (q >> 2)
-          fwd_stepR<L, R>(taps, [&](int q) { return w[q + (q >> 2)]; }, lo, hi);
+          if constexpr (L <= kXorMaxL) {
+            fwd_stepR<L, R>(taps, [&](int q) { return cur[fl<L>(R * g + q)]; }, lo, hi);
+          } else {
+            const double2* w = cur + pad2(R * g);   // pad2(4g + q) == 5g + q + (q >> 2)
+            fwd_stepR<L, R>(taps, [&](int q) { return w[q + (q >> 2)]; }, lo, hi);
+          }
           if (!last) {
-            nxt[pad2(2 * g)] = make_double2(lo[0], lo[1]);
-            nxt[pad2(2 * g + 1)] = make_double2(lo[2], lo[3]);
+            nxt[fl<L>(2 * g)] = make_double2(lo[0], lo[1]);
+            nxt[fl<L>(2 * g + 1)] = make_double2(lo[2], lo[3]);
           } else {
             st_global_v4(dA + R * g, lo[0], lo[1], lo[2], lo[3]);
           }
           if (R * g < n_det) st_global_v4(dD + R * g, hi[0], hi[1], hi[2], hi[3]);
         } else {
           static_assert(R == 2 || R == 4, "R is 2 or 4");
-          fwd_stepR<L, R>(taps, [&](int q) { return cur[pad2(R * g + q)]; }, lo, hi);
-          if (!last) nxt[pad2(g)] = make_double2(lo[0], lo[1]);
+          fwd_stepR<L, R>(taps, [&](int q) { return cur[fl<L>(R * g + q)]; }, lo, hi);
+          if (!last) nxt[fl<L>(g)] = make_double2(lo[0], lo[1]);
           else *reinterpret_cast<double2*>(dA + R * g) = make_double2(lo[0], lo[1]);
           if (R * g < n_det) *reinterpret_cast<double2*>(dD + R * g) = make_double2(hi[0], hi[1]);
         }
@@ -155,8 +176,8 @@ static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, FwtFwdArgs a, bool r
   if (!resident) {
     const int H0 = ((1 << a.m) - 1) * (L - 2);
     const int H1 = ((1 << (a.m - 1)) - 1) * (L - 2);
-    a.cap0 = pad2_size((a.T + H0) / 2 + 4);
-    a.cap1 = pad2_size(((a.T >> 1) + H1) / 2 + 4);
+    a.cap0 = fl_size<L>((a.T + H0) / 2 + 4);
+    a.cap1 = fl_size<L>(((a.T >> 1) + H1) / 2 + 4);
     smem = size_t(a.cap0 + a.cap1) * sizeof(double2);
     a.tiles_per_line = a.h / a.T;
     const int64_t ctas = a.lines * a.tiles_per_line;

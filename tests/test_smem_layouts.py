@@ -35,10 +35,10 @@ def test_forward_windows_and_stores_pad2():
     # k_fwt_fwd, R = 4: lane g reads double2 4g + q of the window (q = 0 .. L/2 + 2)
     for q in range(0, 23):
         assert wavefronts([pad2(4 * g) + q + (q >> 2) for g in range(32)]) == 4
-    # Known cost of the padded layout (the forward kernel's residual bank conflicts in the ncu captures):
-    # the cp.async staging (consecutive slots) and the a_k stores (2 slots per lane) are 2-way.  The
-    # forward tile kernel runs at the HBM copy peak regardless; an XOR layout k ^ ((k >> 3) & 3) would
-    # make all three patterns conflict-free and is checked here as the candidate for the next round.
+    # Cost of the padded layout (long filters keep it; it was the forward kernel's residual bank conflicts
+    # in the ncu captures): the cp.async staging (consecutive slots) and the a_k stores (2 slots per lane)
+    # are 2-way.  Filters up to 24 taps use k ^ ((k >> 3) & 3) (fl, jwc_fwt_fwd.cu): all three patterns
+    # conflict-free.
     assert wavefronts([pad2(k) for k in range(32)]) == 8
     assert all(wavefronts([pad2(2 * g + e) for g in range(32)]) == 8 for e in range(2))
     xor = lambda k: k ^ ((k >> 3) & 3)
