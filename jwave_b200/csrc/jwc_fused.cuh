@@ -9,11 +9,14 @@ namespace jwc {
 constexpr int kThreads = 256;  // upper bound of the CTA size of the strided kernels (launch bound)
 constexpr int kR = 4;          // consecutive outputs (per filter) one thread produces per step
 
-// Shared-memory layout of a line segment: interleaved samples as double2 (x[2k], x[2k+1]), one
+// Padded shared-memory layout of a line segment: interleaved samples as double2 (x[2k], x[2k+1]), one
 // pad slot after every 4 double2.  A thread that produces outputs 4g..4g+3 reads the window
 // k = 4g .. 4g + L/2 + 2; consecutive threads are 5 slots (80 B) apart, so the 8 lanes of a
 // quarter-warp LDS.128 phase hit 8 distinct 16-byte bank groups (20 t mod 32 words is a
-// permutation) - no bank conflicts.
+// permutation) - no bank conflicts on the window loads; staging and 2-slot stores are 2-way.  Used by
+// the resident kernels, the forward tile kernel for long filters and the WPT reverse kernel; the
+// forward tile kernel for L <= 24 (fl, jwc_fwt_fwd.cu) and the FWT reverse kernels (lay, jwc_fwt_rev.cu)
+// use XOR layouts instead (tests/test_smem_layouts.py enumerates all of them).
 __device__ __forceinline__ int pad2(int k2) { return k2 + (k2 >> 2); }
 __host__ __device__ constexpr int pad2_size(int n2) { return n2 + (n2 >> 2) + 1; }
 

@@ -6,7 +6,8 @@
 //
 //   tile mode      (h > res_cap) : one CTA = one tile of T level-0 samples of one line plus a
 //                                 right-hand periodic halo of (2^m - 1)(L - 2) samples; details
-//                                 d_1..d_m go to their final place, a_m to `dstA`.
+//                                 d_1..d_m go to their final place, a_m to `dstA`.  For L <= 24 the
+//                                 halo approximations of every level are a tail warp's job.
 //   resident mode  (h <= res_cap): one CTA = G whole lines; the periodic wrap is an index mask, so
 //                                 every remaining level (down to h = 2) runs in this launch.
 //
