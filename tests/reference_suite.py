@@ -55,6 +55,26 @@ def check_haar_filters():
     assert_array(KAT["filter_db4_dec_hi"], d2.getWaveletDeComposition(), 1e-10)
 
 
+def check_unused_reference_fixtures(make):
+    """Fixture files that sit beside the ones above in T/../resources/testdata but that no reference test
+    reads: filter_db2_dec_lo.txt (a 2-tap filter, i.e. Haar), haar_constant_input.txt and
+    haar_linear_input.txt (inputs without expected outputs).  They still pin something: the 2-tap table, and
+    the closed forms of a Haar level on a constant (details 0, approximations c * sqrt 2) and on a ramp
+    (details -1 / sqrt 2, approximations (4 i + 1) / sqrt 2)."""
+    assert_array(KAT["filter_db2_dec_lo"], WaveletBuilder.create("Haar").getScalingDeComposition(), 1e-10)
+    t = Transform(make("fwt", "Haar1"))
+    c = np.array(KAT["haar_constant_input"])
+    out = t.forward(c, 1)
+    assert_array(c[:4] * math.sqrt(2.0), out[:4], 1e-10)
+    assert_array(np.zeros(4), out[4:], 1e-10)
+    assert_array(c, t.reverse(out, 1), 1e-10)
+    r = np.array(KAT["haar_linear_input"])
+    out = t.forward(r, 1)
+    assert_array((4.0 * np.arange(4) + 1.0) / math.sqrt(2.0), out[:4], 1e-10)
+    assert_array(np.full(4, -1.0 / math.sqrt(2.0)), out[4:], 1e-10)
+    assert_array(r, t.reverse(out, 1), 1e-10)
+
+
 def ladder(n, level):
     """All-ones input: level l gives 2^(l/2) on the first n / 2^l entries, 0 elsewhere."""
     out = np.zeros(n)

@@ -38,6 +38,7 @@ def close(gpu, cpu, scale):
 
 def test_ref_haar_known_answer():
     rs.check_haar_kat(make)
+    rs.check_unused_reference_fixtures(make)
 
 
 @pytest.mark.parametrize("cls", rs.CREATE2ARR)

@@ -31,6 +31,10 @@ def test_filter_fixtures():
     rs.check_haar_filters()
 
 
+def test_fixture_files_no_reference_test_reads():
+    rs.check_unused_reference_fixtures(make)
+
+
 @pytest.mark.parametrize("cls", rs.ORTHONORMAL)
 def test_tap_identities(cls):
     """sum h = sqrt 2 (Legendre: -sqrt 2), g[i] = (-1)^i h[L-1-i], recon == decomp; and
