@@ -79,38 +79,55 @@ extern "C" int jwc_create(jwc_ctx** out, int device) {
   const char* fg = getenv("JWC_FORCE_GENERIC");
   ctx->force_generic = fg && fg[0] == '1';
   if (const char* tune = getenv("JWC_TUNE")) {
-    auto get = [&](const char* key, int* dst) {
-      const char* p = strstr(tune, key);
-      if (p && p[strlen(key)] == '=') {
-        const int v = atoi(p + strlen(key) + 1);
-        if (v >= 0) *dst = v;
-      }
+    // "key=value,key=value": whole-key comparison (rev_tile must not match str_rev_tile), values checked
+    struct Key { const char* name; int* dst; bool pow2; int lo, hi; };
+    const Key keys[] = {
+        {"fwd_tile", &ctx->fwd_tile, true, 256, 1 << 16},     {"fwd_m", &ctx->fwd_m, false, 0, 12},
+        {"fwd_r", &ctx->fwd_r, true, 2, 8},                   {"rev_tile", &ctx->rev_tile, true, 256, 1 << 16},
+        {"rev_m", &ctx->rev_m, false, 1, 12},                 {"rev_rs", &ctx->rev_rs, true, 2, 8},
+        {"fwd_threads", &ctx->fwd_threads, false, 32, 1024},  {"rev_threads", &ctx->rev_threads, false, 32, 384},
+        {"res_cap", &ctx->res_cap, true, 16, 1 << 14},        {"res_threads", &ctx->res_threads, false, 32, 1024},
+        {"wpt_tile", &ctx->wpt_tile, true, 256, 1 << 16},     {"wpt_m", &ctx->wpt_m, false, 1, 12},
+        {"wpt_rs", &ctx->wpt_rs, true, 4, 8},                 {"wpt_r", &ctx->wpt_r, true, 4, 8},
+        {"wpt_threads", &ctx->wpt_threads, false, 64, 512},   {"wpt_inplace", &ctx->wpt_inplace, false, 0, 1},
+        {"rev_tail", &ctx->rev_tail, false, 0, 1},            {"fwd_tail", &ctx->fwd_tail, false, 0, 1},
+        {"str_tile", &ctx->str_tile, true, 128, 1 << 14},     {"str_rev_tile", &ctx->str_rev_tile, true, 128, 1 << 14},
+        {"str_rev_m", &ctx->str_rev_m, false, 1, 12},         {"str_cap", &ctx->str_cap, true, 16, 1 << 14},
+        {"str_threads", &ctx->str_threads, false, 32, 256},   {"str_rev_threads", &ctx->str_rev_threads, false, 32, 256},
+        {"str_tma", &ctx->str_tma, false, 0, 1},              {"str_v2", &ctx->str_v2, false, 0, 1},
+        {"str2_tile", &ctx->str2_tile, true, 128, 1 << 12},   {"str2_rev_tile", &ctx->str2_rev_tile, true, 128, 1 << 12},
+        {"str2_cap", &ctx->str2_cap, true, 16, 1 << 11},      {"str2_m", &ctx->str2_m, false, 0, 8},
+        {"str2_rev_m", &ctx->str2_rev_m, false, 0, 8},        {"fuse_tail", &ctx->fuse_tail, false, 0, 1},
     };
-    get("fwd_tile", &ctx->fwd_tile);
-    get("fwd_m", &ctx->fwd_m);
-    get("fwd_r", &ctx->fwd_r);
-    get("rev_tile", &ctx->rev_tile);
-    get("rev_m", &ctx->rev_m);
-    get("rev_rs", &ctx->rev_rs);
-    get("fwd_threads", &ctx->fwd_threads);
-    get("rev_threads", &ctx->rev_threads);
-    get("res_cap", &ctx->res_cap);
-    get("res_threads", &ctx->res_threads);
-    get("wpt_tile", &ctx->wpt_tile);
-    get("wpt_m", &ctx->wpt_m);
-    get("wpt_rs", &ctx->wpt_rs);
-    get("wpt_r", &ctx->wpt_r);
-    get("str_tile", &ctx->str_tile);
-    get("str_rev_tile", &ctx->str_rev_tile);
-    get("str_rev_m", &ctx->str_rev_m);
-    get("str_cap", &ctx->str_cap);
-    get("str_threads", &ctx->str_threads);
-    get("str_rev_threads", &ctx->str_rev_threads);
-    get("str_tma", &ctx->str_tma);
-    get("wpt_threads", &ctx->wpt_threads);
-    get("wpt_inplace", &ctx->wpt_inplace);
-    get("rev_tail", &ctx->rev_tail);
-    get("fwd_tail", &ctx->fwd_tail);
+    std::string bad;
+    const char* p = tune;
+    while (*p) {
+      const char* end = strchr(p, ',');
+      const std::string tok = end ? std::string(p, end) : std::string(p);
+      p = end ? end + 1 : p + tok.size();
+      if (tok.empty()) continue;
+      const size_t eq = tok.find('=');
+      bool ok = false;
+      if (eq != std::string::npos && eq + 1 < tok.size()) {
+        const std::string name = tok.substr(0, eq);
+        char* rest = nullptr;
+        const long v = strtol(tok.c_str() + eq + 1, &rest, 10);
+        for (const Key& k : keys) {
+          if (name != k.name) continue;
+          ok = rest && *rest == 0 && v >= k.lo && v <= k.hi && (!k.pow2 || (v & (v - 1)) == 0) &&
+               (strstr(k.name, "threads") == nullptr || v % 32 == 0);
+          if (ok) *k.dst = int(v);
+          break;
+        }
+      }
+      if (!ok && bad.empty()) bad = tok;
+    }
+    if (!bad.empty()) {
+      jwc_destroy(ctx);
+      std::lock_guard<std::mutex> lk(g_create_mu);
+      g_create_err = "jwc_create: bad JWC_TUNE entry '" + bad + "' (unknown key, or value out of range / not a power of two)";
+      return JWC_ERR_ARG;
+    }
   }
   *out = ctx;
   return JWC_OK;

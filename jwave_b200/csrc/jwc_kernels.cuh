@@ -67,8 +67,16 @@ struct FwtRevStrArgs {
   // filled in by the launcher
   int tiles_per_line, cblocks, ru, rowsC, rowsP[2];
   int F[kMaxFuse + 2], s0[kMaxFuse + 1], len[kMaxFuse + 1], offD[kMaxFuse + 1], offA[2];
+  int64_t rowsA_per_o, rowsD_per_o;           // tensor rows between consecutive `outer` slices (TMA path)
 };
 cudaError_t launch_fwt_rev_str(jwc_ctx* ctx, int L, const Taps& taps, const FwtRevStrArgs& a, bool resident);
+
+// Second generation (jwc_fwt_strided2.cu): 16 columns per CTA, two per thread, levels in place, TMA-staged
+// in both directions.  Same argument blocks (offD / rowsC count ROWS there).  cudaErrorNotSupported = the
+// shape is not covered (inner % 16, box alignment, CTA size): nothing was launched, use the first generation.
+int fwt_str2_tile_levels(int L, int T, int want);
+cudaError_t launch_fwt_fwd_str2(jwc_ctx* ctx, int L, const Taps& taps, const FwtFwdStrArgs& a, bool resident);
+cudaError_t launch_fwt_rev_str2(jwc_ctx* ctx, int L, const Taps& taps, const FwtRevStrArgs& a, bool resident);
 
 // ---- forward WPT, contiguous lines (jwc_wpt_fwd.cu) -----------------------------------------
 struct WptFwdArgs {

@@ -95,8 +95,11 @@ static bool strided_ok(const jwc_ctx* ctx, const double* in, const double* out, 
 
 static cudaError_t fwt_forward_strided(jwc_ctx* ctx, const WaveletRec& w, const double* in, double* out,
                                        int64_t outer, int n, int64_t inner, int level) {
-  const int cap = ctx->str_cap, tileT = ctx->str_tile;
-  const int m_tile = fwt_str_tile_levels(w.L, tileT);
+  // second generation (jwc_fwt_strided2.cu) where the geometry allows; it declines per launch with
+  // cudaErrorNotSupported and the first generation, which takes the same pass, runs instead
+  const bool v2 = ctx->str_v2 && inner % 16 == 0;
+  const int cap = v2 ? ctx->str2_cap : ctx->str_cap, tileT = v2 ? ctx->str2_tile : ctx->str_tile;
+  const int m_tile = v2 ? fwt_str2_tile_levels(w.L, tileT, ctx->str2_m) : fwt_str_tile_levels(w.L, tileT);
   double* S[2] = {nullptr, nullptr};
   if (n > cap && level > m_tile) {
     JWC_TRY(ensure_scratch(ctx, 1, size_t(outer) * (n >> m_tile) * inner * sizeof(double), &S[1]));
@@ -118,7 +121,9 @@ static cudaError_t fwt_forward_strided(jwc_ctx* ctx, const WaveletRec& w, const 
     a.rmA = (last && ctx->remote) ? *ctx->remote : RemoteMap();  // a_m is final only in the last pass
     a.dstA = last ? out : S[(pass + 1) & 1];
     a.dstA_os = last ? int64_t(n) * inner : int64_t(h >> a.m) * inner;
-    JWC_TRY(launch_fwt_fwd_str(ctx, w.L, w.de, a, resident));
+    cudaError_t e = v2 ? launch_fwt_fwd_str2(ctx, w.L, w.de, a, resident) : cudaErrorNotSupported;
+    if (e == cudaErrorNotSupported) e = launch_fwt_fwd_str(ctx, w.L, w.de, a, resident);
+    JWC_TRY(e);
     a.src = a.dstA; a.src_os = a.dstA_os;
     h >>= a.m; left -= a.m; ++pass;
   }
@@ -131,13 +136,15 @@ static cudaError_t fwt_reverse_strided(jwc_ctx* ctx, const WaveletRec& w, const 
   Pass passes[32];
   int npass = 0;
   size_t need[2] = {0, 0};
-  const int cap = ctx->str_cap, tileT = ctx->str_rev_tile;
+  const bool v2 = ctx->str_v2 && inner % 16 == 0;
+  const int cap = v2 ? ctx->str2_cap : ctx->str_cap, tileT = v2 ? ctx->str2_rev_tile : ctx->str_rev_tile;
   // long filters are FP64-bound and every fused level adds a mostly idle step to each tile: fewer
   // levels per pass measured faster there (Daubechies20 columns: 2 levels 0.50, 5 levels 0.45)
   int rev_m = ctx->str_rev_m;
   const int cap_m = w.L >= 20 ? 2 : (w.L >= 12 ? 3 : rev_m);
   if (rev_m > cap_m) rev_m = cap_m;
-  while ((tileT >> rev_m) < 4) --rev_m;
+  if (v2 && ctx->str2_rev_m > 0) rev_m = ctx->str2_rev_m;
+  while ((tileT >> rev_m) < (v2 ? 8 : 4)) --rev_m;  // a tile keeps at least one group / one TMA box at its coarsest level
   int widths[32];
   int nw = 0;
   const int cur0 = n >> level;
@@ -174,7 +181,9 @@ static cudaError_t fwt_reverse_strided(jwc_ctx* ctx, const WaveletRec& w, const 
     a.dst = last ? out : S[i & 1];
     a.dst_os = last ? int64_t(n) * inner : int64_t(p.h0) * inner;
     a.rm = (last && ctx->remote) ? *ctx->remote : RemoteMap();
-    JWC_TRY(launch_fwt_rev_str(ctx, w.L, w.re, a, p.resident));
+    cudaError_t e = v2 ? launch_fwt_rev_str2(ctx, w.L, w.re, a, p.resident) : cudaErrorNotSupported;
+    if (e == cudaErrorNotSupported) e = launch_fwt_rev_str(ctx, w.L, w.re, a, p.resident);
+    JWC_TRY(e);
     a.srcA = a.dst; a.srcA_os = a.dst_os;
   }
   return cudaSuccess;

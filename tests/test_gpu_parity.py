@@ -149,6 +149,31 @@ def test_strided_axis_tile_and_resident(cls):
     dev.close()
 
 
+@pytest.mark.parametrize("cls", ["Haar1", "Daubechies2", "Daubechies4", "Symlet8", "Coiflet5", "Daubechies20"])
+def test_strided_axis_second_generation_shapes(cls):
+    """inner % 16 == 0 takes the 16-column kernels (jwc_fwt_strided2.cu): tile passes + resident tail, lines
+    that are resident from the start, lines shorter than one TMA box (declined -> first generation), partial
+    depth (the last tile pass is not followed by a resident pass), several column blocks and outer slices."""
+    import torch
+    from jwave_b200.device import DeviceTransforms
+    dev = DeviceTransforms(jw.WaveletBuilder.create(cls))
+    shapes = ((2, 4096, 32, 12), (1, 1024, 48, 10), (3, 512, 16, 9), (1, 8192, 16, 13), (2, 64, 32, 6),
+              (2, 32, 16, 5), (1, 16, 16, 4), (1, 2048, 64, 3), (2, 1024, 16, 1), (2, 8, 16, 3), (1, 2048, 16, 6))
+    for outer, n, inner, level in shapes:
+        x = rng_signal(n + inner + level, outer, n, inner)
+        def columns(direction, arr):
+            lines = np.ascontiguousarray(arr.transpose(0, 2, 1).reshape(-1, n))
+            res = co.batch_1d(co.FWT, direction, cls, lines, level)
+            return np.ascontiguousarray(res.reshape(outer, inner, n).transpose(0, 2, 1))
+        ref = columns(co.FORWARD, x)
+        fd = dev.axis(_lib.FWT, _lib.FORWARD, torch.from_numpy(x).cuda(), outer, n, inner, level)
+        close(fd.cpu().numpy(), ref, np.abs(x).max())
+        back = columns(co.REVERSE, ref)
+        rd = dev.axis(_lib.FWT, _lib.REVERSE, torch.from_numpy(ref).cuda(), outer, n, inner, level)
+        close(rd.cpu().numpy(), back, np.abs(ref).max())
+    dev.close()
+
+
 def test_2d_equals_row_by_row_composition():
     """The whole-array 2-D pass equals BasicTransform's row-by-row driver over the GPU 1-D
     transform (BasicTransform.java:361-399) - same kernels, so bit-equal up to tile effects."""
