@@ -56,19 +56,35 @@ k_fwt_fwd_str2(const __grid_constant__ Taps taps, const __grid_constant__ FwtFwd
   const int n0 = RESIDENT ? h + (L - 2) : T + ((1 << m) - 1) * (L - 2);
 
   // ---- stage: TMA boxes {16 columns, kBoxF rows}; rows past the end of the line wrap to its first row,
-  // always at a box boundary (T and h are multiples of the box height)
-  if (tid == 0) mbar_init(bar, 1);
-  __syncthreads();
+  // always at a box boundary (T and h are multiples of the box height).  The boxes are counted on up to
+  // kStagesF mbarriers in row order: round r of the first level waits only for the rows ITS windows read
+  // (stage min(r, kStagesF - 1)), so a CTA computes from the first third of its tile while the rest is in flight.
   const int boxes = (n0 + kBoxF - 1) / kBoxF;
-  if (tid == 0) mbar_expect_tx(bar, unsigned(boxes) * kBoxF * kC2 * sizeof(double));
+  const int rounds1 = a.rounds1;  // rounds of the first level
+  auto stage_end = [&](int s) {   // first box NOT in stages 0 .. s
+    if (s >= kStagesF - 1 || s >= rounds1 - 1) return boxes;
+    return min(boxes, (2 * R * (s + 1) * ngrp + L - 2 + kBoxF - 1) / kBoxF);
+  };
+  if (tid == 0) {
+    for (int s = 0; s < kStagesF; ++s) mbar_init(&bar[s], 1);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int s = 0, b0 = 0; s < kStagesF; ++s) {
+      const int b1 = stage_end(s);
+      mbar_expect_tx(&bar[s], unsigned(b1 - b0) * kBoxF * kC2 * sizeof(double));
+      b0 = b1;
+    }
+  }
   if ((tid & 31) == 0) {  // one issuing lane per warp
     const int64_t row0 = o * a.rows_per_o;
     for (int bx = tid >> 5; bx < boxes; bx += blockDim.x >> 5) {
+      int st = 0;
+      while (bx >= stage_end(st)) ++st;
       const int s = (tile * T + bx * kBoxF) & (h - 1);
-      tma_load_box(X + size_t(bx) * kBoxF * kL8, &tmap, cb * kC2, int(row0 + s), bar);
+      tma_load_box(X + size_t(bx) * kBoxF * kL8, &tmap, cb * kC2, int(row0 + s), &bar[st]);
     }
   }
-  mbar_wait(bar, 0);
 
   const int z = tap_phase<L, true>();
   for (int k = 1; k <= m; ++k) {
@@ -80,7 +96,8 @@ k_fwt_fwd_str2(const __grid_constant__ Taps taps, const __grid_constant__ FwtFwd
     if (!RESIDENT || n_det >= R) {
       const int gkeep = n_det / R;
       const int groups = RESIDENT ? gkeep : (n_det + ((1 << (m - k)) - 1) * (L - 2) + R - 1) / R;
-      for (int g0 = 0; g0 < groups; g0 += ngrp) {
+      for (int g0 = 0, round = 0; g0 < groups; g0 += ngrp, ++round) {
+        if (k == 1) mbar_wait(&bar[min(round, kStagesF - 1)], 0);
         const int g = g0 + grp;
         const bool has = g < groups;
         double2 lo[R], hi[R];
@@ -107,6 +124,7 @@ k_fwt_fwd_str2(const __grid_constant__ Taps taps, const __grid_constant__ FwtFwd
       }
     } else {
       // resident, h_in = 2 or 4: one output row per thread group, true modular wrap
+      if (k == 1) mbar_wait(&bar[kStagesF - 1], 0);
       const int mask = h_in - 1;
       double2 lo = make_double2(0.0, 0.0), hi = lo;
       const bool has = grp < n_det;
@@ -180,22 +198,17 @@ k_fwt_rev_str2(const __grid_constant__ Taps taps, const __grid_constant__ FwtRev
         mbar_expect_tx(&bar[k], unsigned(a.len[k]) * (k == m ? 2u : 1u) * kC2 * sizeof(double));
     }
     if ((tid & 31) == 0) {
+      // every warp's first lane issues its share of every level's boxes (box j of a level: warps j mod nwarp),
+      // coarsest level first
       const int64_t rowD0 = o * a.rowsD_per_o, rowA0 = o * a.rowsA_per_o;
-      int idx = 0;
       for (int k = m; k >= 1; --k) {
         const int wk = h0 >> k;
         const int O = (k == m) ? ((t0 >> k) - a.F[k] - a.ru) : 2 * ((t0 >> (k + 1)) - a.F[k + 1]);
         const int nb = a.len[k] / kBoxR;
-        for (int j = 0; j < nb; ++j) {
+        for (int j = warp; j < nb; j += nwarp) {
           const int slot = (O + j * kBoxR) & (wk - 1);
-          if (k == m) {
-            if (idx % nwarp == warp)
-              tma_load_box(X + size_t(j) * kBoxR * kL8, &tmapA, cb * kC2, int(rowA0 + slot), &bar[k]);
-            ++idx;
-          }
-          if (idx % nwarp == warp)
-            tma_load_box(X + size_t(a.offD[k] + j * kBoxR) * kL8, &tmapD, cb * kC2, int(rowD0 + wk + slot), &bar[k]);
-          ++idx;
+          if (k == m) tma_load_box(X + size_t(j) * kBoxR * kL8, &tmapA, cb * kC2, int(rowA0 + slot), &bar[k]);
+          tma_load_box(X + size_t(a.offD[k] + j * kBoxR) * kL8, &tmapD, cb * kC2, int(rowD0 + wk + slot), &bar[k]);
         }
       }
     }
@@ -220,8 +233,9 @@ k_fwt_rev_str2(const __grid_constant__ Taps taps, const __grid_constant__ FwtRev
           for (int e = 0; e < 2 * R; ++e) X[(2 * R * grp + e) * kL8 + l8] = t[e];
         }
         __syncthreads();
-      } else {
-        for (int g = grp; g < groups; g += ngrp) {
+      } else if (tid < a.nmain) {
+        // level 1 (no left extension): the main warps only - whole multiples of 4 warps, see the launcher
+        for (int g = grp; g < groups; g += a.nmain >> 3) {
           double2 t[2 * R];
           const int top = s0 + R * g + R - 1;
           const double2* wa = X + top * kL8 + l8;
@@ -366,9 +380,16 @@ static cudaError_t launch_fwd2_L(jwc_ctx* ctx, const Taps& taps, FwtFwdStrArgs a
     a.tiles_per_line = 1;
     grid = a.outer * a.cblocks;
   }
-  // two rounds at the first (largest) level
-  const int nthr = min(resident ? kMaxThrRes2 : kMaxThr2, max(64, round_up2((groups1 + 1) / 2 * kL8, 32)));
-  const size_t smem = size_t(a.rows0) * kC2 * sizeof(double) + 16;  // + the mbarrier
+  // Tile mode: T / 2 threads = whole multiples of 4 warps (warps map round-robin onto the 4 sub-partitions of
+  // an SM; with 10 warps two sub-partitions carried 3 and two carried 2, and the per-level barriers turned
+  // that into 17 % idle FP64 pipe, profiles/r02_ncu_c4_str2_first.md).  The kept groups of every level then
+  // fill whole rounds (2 at level 1, 1 at level 2, ...) and the halo groups, low pass only, are one more short
+  // round.  Resident mode: two rounds at the first level.
+  int nthr;
+  if (!resident) nthr = max(128, min(256, a.T / 2 / 128 * 128));
+  else nthr = min(kMaxThrRes2, max(64, round_up2((groups1 + 1) / 2 * kL8, 32)));
+  a.rounds1 = (groups1 + nthr / kL8 - 1) / (nthr / kL8);
+  const size_t smem = size_t(a.rows0) * kC2 * sizeof(double) + kStagesF * sizeof(uint64_t);  // + the mbarriers
   if (nthr > (resident ? kMaxThrRes2 : kMaxThr2) || smem > ctx->smem_optin || grid > 0x7fffffff || grid < 1) return cudaErrorNotSupported;
   CUtensorMap tmap;
   if (!make_tmap2(&tmap, a.src, a.outer * a.rows_per_o, a.inner, kBoxF)) return cudaErrorNotSupported;
@@ -429,7 +450,11 @@ static cudaError_t launch_rev2_L(jwc_ctx* ctx, const Taps& taps, FwtRevStrArgs a
       end = a.offD[k] + a.len[k];
     }
     a.rowsC = end;
-    nthr = max(128, round_up2(gmax * kL8, 32));
+    // main warps: T / 2 threads (whole multiples of 4 warps: the SM's 4 sub-partitions stay balanced) take the
+    // kept groups - one round at level 2, two at level 1; the left-extension groups of the levels that hold
+    // their results in registers go to one extra warp
+    a.nmain = max(128, min(256, a.T / 2 / 128 * 128));
+    nthr = max(a.nmain, round_up2(gmax * kL8, 32));
     a.tiles_per_line = a.h0 / a.T;
     grid = a.outer * a.tiles_per_line * a.cblocks;
   } else {

@@ -53,6 +53,7 @@ struct FwtFwdStrArgs {
   RemoteMap rmD, rmA;                         // mode 1: the d_k rows / the a_m rows go to peer slabs
   int tiles_per_line, cblocks, rows0, rows1;  // filled in by the launcher
   int64_t rows_per_o;                         // tensor rows between consecutive `outer` slices (TMA path)
+  int rounds1;                                // second generation: rounds of the first level
 };
 int fwt_str_tile_levels(int L, int T);
 cudaError_t launch_fwt_fwd_str(jwc_ctx* ctx, int L, const Taps& taps, const FwtFwdStrArgs& a, bool resident);
@@ -68,6 +69,7 @@ struct FwtRevStrArgs {
   int tiles_per_line, cblocks, ru, rowsC, rowsP[2];
   int F[kMaxFuse + 2], s0[kMaxFuse + 1], len[kMaxFuse + 1], offD[kMaxFuse + 1], offA[2];
   int64_t rowsA_per_o, rowsD_per_o;           // tensor rows between consecutive `outer` slices (TMA path)
+  int nmain;                                  // second generation: threads that take level 1
 };
 cudaError_t launch_fwt_rev_str(jwc_ctx* ctx, int L, const Taps& taps, const FwtRevStrArgs& a, bool resident);
 

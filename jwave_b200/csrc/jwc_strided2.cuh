@@ -23,6 +23,7 @@ constexpr int kC2 = 16;        // columns per CTA
 constexpr int kL8 = 8;         // threads per row (two columns each) == double2 per row
 constexpr int kR2 = 4;         // outputs (forward) / slots (reverse) of one task
 constexpr int kBoxF = 16;      // TMA box rows: forward staging (2 KB boxes)
+constexpr int kStagesF = 4;     // forward staging: mbarriers the boxes are counted on, in row order
 constexpr int kBoxR = 8;       // reverse staging (1 KB boxes: the left extensions are 8-row aligned)
 constexpr int kMaxThr2 = 320;   // tile-mode CTA size bound: 2 CTAs per SM at <= 96 registers
 constexpr int kMaxThrRes2 = 256;  // resident-mode CTA size bound (lines of up to 512 rows)

@@ -71,6 +71,7 @@ def lib():
         L.jwo_parallel_wpt.argtypes = [C.c_int, _wp, _dp, C.c_long, C.c_int, C.c_int, _dp, C.c_int]
         L.jwo_parallel_2d.argtypes = [C.c_int, C.c_int, _wp, _dp, C.c_long, C.c_int, C.c_int, C.c_int,
                                       C.c_int, _dp, C.c_int]
+        L.jwo_parallel_3d.argtypes = [C.c_int, C.c_int, _wp, _dp] + [C.c_int] * 6 + [_dp, C.c_int]
         L.jwo_decompose.argtypes = [C.c_int, C.POINTER(C.c_int)]
         L.jwo_aed.argtypes = [C.c_int, C.c_int, _wp, _dp, C.c_int, _dp]
         L.jwo_compress_magnitude.restype = C.c_double
@@ -185,6 +186,15 @@ def parallel_2d(kind, direction, name, x, lvlM, lvlN, threads=0):
     out = np.empty_like(x)
     b, rows, cols = x.shape
     _check(lib().jwo_parallel_2d(kind, direction, wavelet(name), _p(x), b, rows, cols, lvlM, lvlN, _p(out), threads))
+    return out
+
+
+def parallel_3d(kind, direction, name, s, lvlP, lvlQ, lvlR, threads=0):
+    """ParallelTransform.forward/reverse(double[][][], lvlP, lvlQ, lvlR) on all host threads."""
+    s = _in(s)
+    P, Q, R = s.shape
+    out = np.empty_like(s)
+    _check(lib().jwo_parallel_3d(kind, direction, wavelet(name), _p(s), P, Q, R, lvlP, lvlQ, lvlR, _p(out), threads))
     return out
 
 

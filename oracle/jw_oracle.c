@@ -628,6 +628,7 @@ typedef struct {
   double* out;
   int n, level;
   int rows, cols, lvl, do_rows;
+  int P, Q, R, lvlP, lvlQ, lvlR;
   double* arr;
   int h;
   atomic_int status;
@@ -720,6 +721,59 @@ int jwo_parallel_2d(int kind, int dir, const jwo_wavelet* w, const double* in, l
       j.lvl = j.do_rows ? lvlN : lvlM;
       parallel_for(j.do_rows ? rows : cols, 8, nt, body_line, &j);
     }
+  }
+  return atomic_load(&j.status);
+}
+
+static void body_slice(long i, void* ctx) {
+  jwo_job* j = (jwo_job*)ctx;
+  size_t slice = (size_t)j->Q * j->R;
+  note_status(j, jwo_2d(j->kind, j->dir, j->w, j->in + (size_t)i * slice, j->Q, j->R, j->lvlP, j->lvlQ,
+                        j->out + (size_t)i * slice));
+}
+
+/* Space3DTransformTask.computeDirectly (ParallelTransform.java:376-404) for one j: every k, gather along i */
+static void body_pencils(long jj, void* ctx) {
+  jwo_job* j = (jwo_job*)ctx;
+  size_t slice = (size_t)j->Q * j->R;
+  double* a = (double*)malloc(sizeof(double) * (size_t)j->P);
+  double* b = (double*)malloc(sizeof(double) * (size_t)j->P);
+  for (int k = 0; k < j->R; k++) {
+    size_t off = (size_t)jj * j->R + k;
+    for (int i = 0; i < j->P; i++) a[i] = j->in[i * slice + off];
+    int st = jwo_1d(j->kind, j->dir, j->w, a, j->P, j->lvlR, b);
+    note_status(j, st);
+    if (st) break;
+    for (int i = 0; i < j->P; i++) j->out[i * slice + off] = b[i];
+  }
+  free(a);
+  free(b);
+}
+
+/* transforms/ParallelTransform.java:137-173 (forward: every [j][k] slice as a pool task running the 2-D
+ * transform with (lvlP, lvlQ) - the level shift of SURVEY.md F5 is inherited - then the i axis as
+ * Space3DTransformTask over blocks of j, :338-406) and :175-213 (reverse: the i axis FIRST, then the slices -
+ * the opposite order of BasicTransform.java:611-655). */
+int jwo_parallel_3d(int kind, int dir, const jwo_wavelet* w, const double* in, int P, int Q, int R,
+                    int lvlP, int lvlQ, int lvlR, double* out, int threads) {
+  if (P <= 0 || Q <= 0 || R <= 0) return JWO_ERR_ARG;
+  int nt = pick_threads(threads);
+  jwo_job j = {0};
+  j.kind = kind; j.dir = dir; j.w = w; j.P = P; j.Q = Q; j.R = R;
+  j.lvlP = lvlP; j.lvlQ = lvlQ; j.lvlR = lvlR;
+  j.out = out;
+  if (dir == JWO_FORWARD) {
+    j.in = in;
+    parallel_for(P, 1, nt, body_slice, &j);
+    if (atomic_load(&j.status)) return atomic_load(&j.status);
+    j.in = out;
+    parallel_for(Q, 1, nt, body_pencils, &j);
+  } else {
+    j.in = in;
+    parallel_for(Q, 1, nt, body_pencils, &j);
+    if (atomic_load(&j.status)) return atomic_load(&j.status);
+    j.in = out;
+    parallel_for(P, 1, nt, body_slice, &j);
   }
   return atomic_load(&j.status);
 }

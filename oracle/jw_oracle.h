@@ -102,6 +102,10 @@ int jwo_parallel_wpt(int dir, const jwo_wavelet* w, const double* in, long batch
 /* transforms/ParallelTransform.java:70-93, :137-173: rows / columns / slices in parallel */
 int jwo_parallel_2d(int kind, int dir, const jwo_wavelet* w, const double* in, long batch, int rows,
                     int cols, int lvlM, int lvlN, double* out, int threads);
+/* transforms/ParallelTransform.java:137-173, :175-213: slices as pool tasks + the i axis over blocks of j;
+ * the reverse runs the i axis first */
+int jwo_parallel_3d(int kind, int dir, const jwo_wavelet* w, const double* in, int P, int Q, int R,
+                    int lvlP, int lvlQ, int lvlR, double* out, int threads);
 int jwo_max_threads(void);
 
 #ifdef __cplusplus

@@ -198,3 +198,27 @@ def test_compressor_magnitude_restatement():
     assert np.array_equal(out, np.where(np.abs(x) >= mag, x, 0.0))
     out2, _ = co.compress_magnitude(x, 0.1)
     assert np.array_equal(out2, np.where(np.abs(x) >= 0.1 * mag, x, 0.0))
+
+
+def test_parallel_transform_ports_match_the_sequential_drivers():
+    """ParallelTransform (ParallelTransform.java:70-134, :137-213), the CPU baseline of configs 4 and 5: the
+    2-D form and the 3-D forward run the same 1-D transforms in the same axis order as BasicTransform, so they
+    are bit-equal to jwo_2d / jwo_3d; the 3-D reverse runs the outer axis FIRST (:193), which only commutes
+    up to rounding."""
+    rng = np.random.default_rng(11)
+    imgs = rng.standard_normal((3, 32, 64))
+    for direction in (co.FORWARD, co.REVERSE):
+        want = np.stack([co.transform_2d(co.FWT, direction, "Daubechies4", m, 5, 6) for m in imgs])
+        for threads in (1, 4):
+            assert np.array_equal(co.parallel_2d(co.FWT, direction, "Daubechies4", imgs, 5, 6, threads), want)
+    vol = rng.standard_normal((16, 8, 32))
+    for kind in (co.FWT, co.WPT):
+        f = co.transform_3d(kind, co.FORWARD, "Coiflet1", vol, 3, 4, 5)   # (lvlP, lvlQ, lvlR) with the F5 shift
+        for threads in (1, 3):
+            assert np.array_equal(co.parallel_3d(kind, co.FORWARD, "Coiflet1", vol, 3, 4, 5, threads), f)
+        r = co.transform_3d(kind, co.REVERSE, "Coiflet1", f, 3, 4, 5)
+        pr = co.parallel_3d(kind, co.REVERSE, "Coiflet1", f, 3, 4, 5, 4)
+        assert np.abs(pr - r).max() <= 1e-12 * np.abs(f).max()
+        assert np.abs(pr - vol).max() <= 1e-9
+    with pytest.raises(co.OracleError):
+        co.parallel_3d(co.FWT, co.FORWARD, "Haar1", np.zeros((4, 6, 8)), 2, 2, 3)

@@ -143,7 +143,8 @@ def rev_geometry(L, T, m):
     for k in range(m - 1, 0, -1):
         offD[k] = max(end, length[k])
         end = offD[k] + length[k]
-    nthr = max(128, round_up(gmax * 8, 32))
+    nmain = max(128, min(256, T // 2 // 128 * 128))
+    nthr = max(nmain, round_up(gmax * 8, 32))
     return ru, F, length, s0, offD, end, nthr
 
 
@@ -220,6 +221,11 @@ def model_reverse_pass(coef, a_m, h0, T, m, L, lo_t, hi_t, resident):
     return out
 
 
+def fwd_tile_threads(T):
+    """launch_fwd2_L: whole multiples of 4 warps"""
+    return max(128, min(256, T // 2 // 128 * 128))
+
+
 def plan_levels(L, T, want=0):
     m = 1
     while ((m < want) if want > 0 else (((1 << (m + 1)) - 1) * (L - 2) <= T // 4)) and (T >> (m + 1)) >= BOXF:
@@ -244,8 +250,8 @@ def test_forward_model_matches_oracle(L, h, T, cap):
     while left > 0:
         resident = width <= cap or width < T
         m = left if resident else min(left, plan_levels(L, T))
-        groups1 = max(1, (width // 2) // R) if resident else ((T >> 1) + ((1 << (m - 1)) - 1) * (L - 2) + R - 1) // R
-        nthr = min(MAXTHR, max(64, round_up((groups1 + 1) // 2 * 8, 32)))
+        groups1 = max(1, (width // 2) // R)
+        nthr = min(256, max(64, round_up((groups1 + 1) // 2 * 8, 32))) if resident else fwd_tile_threads(T)
         outD, outA = model_forward_pass(src, width, T, m, L, s_de, w_de, resident, nthr // 8)
         for k, d in outD.items():
             got[width >> k:2 * (width >> k)] = d
@@ -284,8 +290,6 @@ def test_reverse_model_matches_oracle(L, h, T, cap):
 def test_launch_shapes_fit_the_cta_bound():
     """Default plan (T = 512): CTA sizes stay within kMaxThr2 for every filter length."""
     for L in range(2, 42, 2):
-        m = plan_levels(L, 512)
-        groups1 = ((512 >> 1) + ((1 << (m - 1)) - 1) * (L - 2) + R - 1) // R
-        assert round_up((groups1 + 1) // 2 * 8, 32) <= MAXTHR
+        assert fwd_tile_threads(512) % 128 == 0 and fwd_tile_threads(512) <= MAXTHR
         rev_m = 2 if L >= 20 else (3 if L >= 12 else 5)
         assert rev_geometry(L, 512, rev_m)[-1] <= MAXTHR
