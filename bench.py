@@ -1,23 +1,30 @@
 #!/usr/bin/env python3
-"""bench.py - the headline benchmark of the JWave wavelet hot path on B200.
+"""bench.py - the benchmark of the JWave wavelet hot path on B200: every BASELINE.json config in one line.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload all|c2|c3|c4|c5] [--impl reference]
 
-Workloads (BASELINE.json `configs`):
-  c2 (default) Daubechies4 FWT 1-D, full depth (14 levels), 65,536 signals x 2^14 fp64 PER GPU
-  c3           Symlet8 WPT 1-D, 6 levels, 4,096 signals x 2^16 fp64 PER GPU
+Workloads (BASELINE.json `configs`; C1, one 2^16 Haar signal, is the reference's CPU-runnable case and a parity test):
+  c2  Daubechies4 FWT 1-D, full depth (14 levels), 65,536 signals x 2^14 fp64 PER GPU        <- the headline line
+  c3  Symlet8 WPT 1-D, 6 levels, 4,096 signals x 2^16 fp64 PER GPU
+  c4  Daubechies20 FWT 2-D, full depth, 64 images of 8192 x 8192 fp64 PER GPU
+  c5  Coiflet5 FWT 3-D, full depth, ONE 1024^3 fp64 volume: on one GPU at N = 1, slab-decomposed over all N
+      GPUs at N > 1 (the only workload with an exchange step), with full-size parity against the oracle
+The default run measures all four: the JSON line's top level is c2 (value, roofline, cpu_baseline, e2e, ...) and
+`workloads` holds the same record for c3, c4 and c5.
 
-One *step* = forward transform of the whole batch followed by the reverse transform of the
-coefficients (the reference's own timing unit: ParallelWPTPerformanceTest.java:270-295).
-`value` = samples transformed per second, counting both directions (2 x batch x n per step),
-inputs resident in HBM.  `e2e` = the same step through the host-buffer C ABI (jwc_fwt1d /
-jwc_wpt1d) with pinned HOST arrays, H2D and D2H inside the timed region.
+One *step* = forward transform of the whole batch followed by the reverse transform of the coefficients (the
+reference's own timing unit: ParallelWPTPerformanceTest.java:270-295).  `value` = samples transformed per second,
+counting both directions, inputs resident in HBM, CUDA-event time, max over ranks.  `e2e` = the same step through
+the host-buffer C ABI (jwc_fwt1d / jwc_wpt1d / jwc_fwt2d / jwc_fwt3d) with pinned HOST arrays, H2D and D2H inside
+the timed region, and the PCIe ceiling measured beside it (concurrent pinned copies on all ranks at once).
 
-N > 1: one process per GPU (torchrun), independent signals sharded by rank, no collective on the
-data path (weak scaling: the per-GPU batch is fixed).  Times are CUDA-event times, max over ranks.
+N > 1: one process per GPU (torchrun).  c2-c4 shard independent signals / images by rank with NO collective on
+the data path: weak scaling (per-GPU batch fixed) for `value` AND for `e2e`.  c5 is one volume over all GPUs
+(strong scaling; stated in its record).
 
---impl reference times the CPU restatement of JWave (oracle/, all host threads) on a bounded
-sample of the same workload.  It is the only code path here that executes oracle/ for timing.
+--impl reference times the CPU restatement of JWave (oracle/, all host threads) on the stated c2 batch (and bounded
+samples of c3-c5).  Together with cpu_sample() it is the only code here that executes oracle/ for timing; the parity
+checks of c5 at N > 1 use it as the checker.
 """
 import argparse
 import json
@@ -38,14 +45,14 @@ WORKLOADS = {
            "Daubechies4 FWT 1-D full depth (14 levels), 65536 signals x 2^14 fp64 per GPU"),
     "c3": ("Symlet8", "wpt", 1 << 16, 6, 4096,
            "Symlet8 WPT 1-D 6 levels, 4096 signals x 2^16 fp64 per GPU"),
-    # 2-D / 3-D configs (device-resident timing only; `n` is the edge length, level = log2 n per axis)
-    "c4": ("Daubechies20", "fwt2d", 8192, 13, 16,
-           "Daubechies20 FWT 2-D full depth, 8192 x 8192 fp64 images, 16 per GPU per step (BASELINE batch: 64)"),
+    "c4": ("Daubechies20", "fwt2d", 8192, 13, 64,
+           "Daubechies20 FWT 2-D full depth (13 + 13 levels), 64 images of 8192 x 8192 fp64 per GPU"),
     "c5": ("Coiflet5", "fwt3d", 1024, 10, 1,
-           "Coiflet5 FWT 3-D full depth on one 1024^3 fp64 volume per GPU (single-GPU form of config 5)"),
+           "Coiflet5 FWT 3-D full depth (10 + 10 + 10 levels) on one 1024^3 fp64 volume"),
 }
 METRIC = "Daub4 FWT / Sym8 WPT GSamples/s at 1-8 B200, % HBM roofline, vs JWave CPU"
 FP64_PEAK_TFLOPS = 36.7  # measured here with tools/microbench.cu (DFMA), see DESIGN.md
+DIMS = {"fwt": 1, "wpt": 1, "fwt2d": 2, "fwt3d": 3}
 
 
 def peaks():
@@ -146,53 +153,81 @@ class ClockSampler:
         return out
 
 
+# ---- CPU side: the oracle port of JWave's own parallel drivers ----------------------------------------------
+
 def oracle_step(co, cls, kind, x, level, threads, pwpt=False):
-    """forward + reverse of a [batch][n] sample on the host cores.  Independent signals run one
-    per task on a fixed pool (the pattern of ParallelizationOpportunityTest.java:79-110) - for the
-    WPT that is what a batch user of the reference gets the most out of.  pwpt=True times the
-    reference's own ParallelWaveletPacketTransform decomposition instead (packets of ONE signal in
-    parallel, signals looped; README: "1.2-1.3x")."""
+    """forward + reverse on the host cores with the reference's own work decomposition:
+      fwt / wpt : independent signals, one per task on a fixed pool (ParallelizationOpportunityTest.java:79-110);
+                  pwpt=True: ParallelWaveletPacketTransform (packets of ONE signal in parallel, signals looped)
+      fwt2d     : ParallelTransform.forward/reverse(double[][]) per image (ParallelTransform.java:70-134)
+      fwt3d     : ParallelTransform.forward/reverse(double[][][]) (ParallelTransform.java:137-213)"""
     if kind == "fwt":
         c = co.batch_1d(co.FWT, co.FORWARD, cls, x, level, threads)
         return co.batch_1d(co.FWT, co.REVERSE, cls, c, level, threads)
-    if pwpt:
-        c = co.parallel_wpt(co.FORWARD, cls, x, level, threads)
-        return co.parallel_wpt(co.REVERSE, cls, c, level, threads)
-    c = co.batch_1d(co.WPT, co.FORWARD, cls, x, level, threads)
-    return co.batch_1d(co.WPT, co.REVERSE, cls, c, level, threads)
+    if kind == "wpt":
+        if pwpt:
+            c = co.parallel_wpt(co.FORWARD, cls, x, level, threads)
+            return co.parallel_wpt(co.REVERSE, cls, c, level, threads)
+        c = co.batch_1d(co.WPT, co.FORWARD, cls, x, level, threads)
+        return co.batch_1d(co.WPT, co.REVERSE, cls, c, level, threads)
+    if kind == "fwt2d":
+        lv = x.shape[-1].bit_length() - 1
+        c = co.parallel_2d(co.FWT, co.FORWARD, cls, x, lv, lv, threads)
+        return co.parallel_2d(co.FWT, co.REVERSE, cls, c, lv, lv, threads)
+    lv = [s.bit_length() - 1 for s in x.shape]
+    c = co.parallel_3d(co.FWT, co.FORWARD, cls, x, lv[0], lv[1], lv[2], threads)
+    return co.parallel_3d(co.FWT, co.REVERSE, cls, c, lv[0], lv[1], lv[2], threads)
 
 
-def cpu_sample(cls, kind, n, level, target_s=2.0, max_signals=None):
-    """Time the oracle on a bounded sample sized for ~target_s of wall time on all host threads."""
+CPU_WHAT = {
+    "fwt": "FastWaveletTransform per signal on a fixed thread pool",
+    "wpt": "WaveletPacketTransform per signal on a fixed thread pool",
+    "fwt2d": "ParallelTransform(FastWaveletTransform) 2-D: rows, then columns, as pool tasks; images looped",
+    "fwt3d": "ParallelTransform(FastWaveletTransform) 3-D: slices as pool tasks, then the outer axis over blocks of j",
+}
+
+
+def cpu_sample(cls, kind, n, level, target_s=8.0, fixed_signals=None):
+    """Time the oracle on a bounded sample of the workload on all host threads (about target_s of CPU wall time;
+    1-D: the number of signals is grown until one step takes that long; 2-D: one full-size image; 3-D: a 512^3
+    volume - an eighth of the samples, same filter, same drivers)."""
     import numpy as np
     from oracle import c_oracle as co
     threads = co.max_threads()
     rng = np.random.default_rng(42)
-    signals = max(threads, 8)
-    oracle_step(co, cls, kind, rng.standard_normal((signals, n)), level, threads)  # warm the pool
-    while True:  # grow the probe until it is long enough to extrapolate from
-        probe = rng.standard_normal((signals, n))
-        t0 = time.perf_counter()
-        oracle_step(co, cls, kind, probe, level, threads)
-        dt = max(time.perf_counter() - t0, 1e-6)
-        if dt >= 0.25 * target_s or signals >= (1 << 15):
-            break
-        signals *= 4
-    signals = int(max(threads, min(signals * target_s / dt, 1 << 16)))
-    if max_signals:
-        signals = min(signals, max_signals)
-    for _ in range(3):
-        x = rng.standard_normal((signals, n))
+    if kind in ("fwt2d", "fwt3d"):
+        shape = (1, n, n) if kind == "fwt2d" else (min(n, 512),) * 3
+        x = rng.standard_normal(shape)
+        small = rng.standard_normal((1, 256, 256) if kind == "fwt2d" else (64, 64, 64))
+        oracle_step(co, cls, kind, small, level, threads)  # warm the pool
         t0 = time.perf_counter()
         oracle_step(co, cls, kind, x, level, threads)
         dt = time.perf_counter() - t0
-        if dt >= 0.5 * target_s or signals >= (max_signals or (1 << 16)):
-            break
-        signals = int(min(signals * target_s / dt, max_signals or (1 << 16)))
+        return {"value": 2.0 * x.size / dt * 1e-9, "unit": "GSamples/s", "cores": threads, "kind": "port",
+                "sample": ("one 8192 x 8192 image" if kind == "fwt2d" else f"one {shape[0]}^3 volume")
+                          + f" (forward+reverse), {dt:.2f} s wall",
+                "what": CPU_WHAT[kind] + " - C restatement of the JWave CPU path, -O2 -ffp-contract=off"}
+    signals = max(threads, 8)
+    oracle_step(co, cls, kind, rng.standard_normal((signals, n)), level, threads)  # warm the pool
+    if fixed_signals:
+        signals = fixed_signals
+    else:
+        while True:  # grow the probe until it is long enough to extrapolate from
+            probe = rng.standard_normal((signals, n))
+            t0 = time.perf_counter()
+            oracle_step(co, cls, kind, probe, level, threads)
+            dt = max(time.perf_counter() - t0, 1e-6)
+            if dt >= 0.1 * target_s or signals >= (1 << 15):
+                break
+            signals *= 4
+        signals = int(max(threads, min(signals * target_s / dt, 1 << 16)))
+    x = rng.standard_normal((signals, n))
+    t0 = time.perf_counter()
+    oracle_step(co, cls, kind, x, level, threads)
+    dt = time.perf_counter() - t0
     out = {"value": 2.0 * signals * n / dt * 1e-9, "unit": "GSamples/s", "cores": threads, "kind": "port",
            "sample": f"{signals} signals x {n} (forward+reverse), {dt:.2f} s wall",
-           "what": ("FastWaveletTransform" if kind == "fwt" else "WaveletPacketTransform") +
-                   " per signal on a fixed thread pool - C restatement of the JWave CPU path, -O2 -ffp-contract=off"}
+           "what": CPU_WHAT[kind] + " - C restatement of the JWave CPU path, -O2 -ffp-contract=off"}
     if kind == "wpt":  # also the reference's own within-signal decomposition, on a small sample
         few = rng.standard_normal((max(2, min(signals, 64)), n))
         oracle_step(co, cls, kind, few[:2], level, threads, pwpt=True)
@@ -204,100 +239,222 @@ def cpu_sample(cls, kind, n, level, target_s=2.0, max_signals=None):
 
 
 def run_reference(args):
-    """--impl reference: the CPU path only (no GPU, none of our kernels)."""
+    """--impl reference: the CPU path only (no GPU, none of our kernels).  Each step transforms the STATED c2 batch
+    (65536 signals x 2^14, forward + reverse) on all host threads; c3-c5 are timed on bounded samples."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     import numpy as np
     from oracle import c_oracle as co
-    cls, kind, n, level, batch, desc = WORKLOADS[args.workload]
+    name = "c2" if args.workload == "all" else args.workload
+    cls, kind, n, level, batch, desc = WORKLOADS[name]
     threads = co.max_threads()
-    base = cpu_sample(cls, kind, n, level, target_s=1.0)
-    signals = int(base["sample"].split()[0])
-    x = np.random.default_rng(42).standard_normal((signals, n))
+    if args.batch:
+        batch = args.batch
+    if DIMS[kind] == 1:
+        # the stated batch, in blocks of 8192 signals (1 GiB) so the host arrays stay small; same work per step
+        block = min(batch, 8192)
+        x = np.random.default_rng(42).standard_normal((block, n))
+        reps = max(1, batch // block)
+
+        def step():
+            for _ in range(reps):
+                oracle_step(co, cls, kind, x, level, threads)
+        samples = reps * block * n
+        sample = f"{reps * block} signals x {n} per step (the stated batch), in blocks of {block}"
+    else:
+        base = cpu_sample(cls, kind, n, level)
+        x = np.random.default_rng(42).standard_normal((1, n, n) if kind == "fwt2d" else (min(n, 512),) * 3)
+
+        def step():
+            oracle_step(co, cls, kind, x, level, threads)
+        samples = x.size
+        sample = base["sample"].split(" (")[0] + " per step"
     for _ in range(args.warmup):
-        oracle_step(co, cls, kind, x, level, threads)
+        step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        oracle_step(co, cls, kind, x, level, threads)
+        step()
     dt = time.perf_counter() - t0
-    value = 2.0 * signals * n * args.steps / dt * 1e-9
+    value = 2.0 * samples * args.steps / dt * 1e-9
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "GSamples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "sample_per_step": f"{signals} signals x {n}", "host_threads": threads},
-        "cpu_baseline": dict(base, value=value, sample=f"{signals} signals x {n} per step, {args.steps} steps"),
+        "config": {"workload": desc, "step": "forward + reverse of the whole batch", "items_per_gpu": batch, "n": n,
+                   "level": level, "wavelet": cls, "sample_per_step": sample, "host_threads": threads},
+        "cpu_baseline": {"value": value, "unit": "GSamples/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample}, {args.steps} steps",
+                         "what": CPU_WHAT[kind] + " - C restatement of the JWave CPU path, -O2 -ffp-contract=off"},
         "e2e": {"value": value, "unit": "GSamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if args.workload == "all" and not args.no_cpu:
+        line["workloads"] = {w: {"cpu_baseline": cpu_sample(*WORKLOADS[w][:4])} for w in ("c3", "c4", "c5")}
     print(json.dumps(line))
     return 0
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2")
-    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--batch", type=int, default=0, help="override signals per GPU (debug only)")
-    ap.add_argument("--slab", choices=["peer", "copies", "all2all"], default="copies",
-                    help="c5 on N > 1 GPUs: peer-mapped slabs filled by strided device copies (default) or by the "
-                         "axis kernels' own stores (peer), or NCCL all-to-all")
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-cpu", action="store_true")
-    args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
+# ---- GPU side -------------------------------------------------------------------------------------------------
 
-    import numpy as np
-    import torch
-    import torch.distributed as dist
+def host_fit(items, bytes_per_item, world, arrays=3, frac=0.4):
+    """Largest power-of-two fraction of `items` whose `arrays` pinned host copies, on all `world` ranks of this
+    box, stay below `frac` of the available host memory."""
+    avail = 64 << 30
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable:"):
+                avail = int(ln.split()[1]) * 1024
+    except Exception:
+        pass
+    while items > 1 and arrays * items * bytes_per_item * world > frac * avail:
+        items //= 2
+    return max(items, 1)
 
-    import jwave_b200 as jw
-    from jwave_b200 import _lib
-    from jwave_b200.device import DeviceTransforms
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
-    torch.cuda.set_device(local)
+def pcie_probe(torch, dist, world, nbytes=1 << 30, reps=4):
+    """Concurrent pinned H2D + D2H on every rank at once: the per-GPU bus ceiling the e2e pipeline works under."""
+    h_in = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d_in = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    d_out = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def both():
+        with torch.cuda.stream(s1):
+            d_in.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_out.copy_(d_out, non_blocking=True)
+    both()
+    torch.cuda.synchronize()
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        both()
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    del h_in, h_out, d_in, d_out
+    return nbytes * reps / float(dt[0]) * 1e-9  # GB/s per direction per GPU, both directions busy
 
-    cls, kind, n, level, batch, desc = WORKLOADS[args.workload]
+
+def slab_parity(torch, dist, np, jw, _lib, make_slab, dev, cls, n, level, rank, world):
+    """c5 at N > 1: parity of the slab-decomposed path against the oracle, visible in the bench line because the
+    driver's test box has one GPU.  (a) a small random volume through the same slab code, gathered and compared
+    with the oracle's 3-D transform; (b) the FULL 1024^3 volume with a separable probe x = u (x) v (x) w: the
+    3-D transform of a rank-one volume is the outer product of the three 1-D transforms (linearity; the axis
+    passes act on different indices), so every rank checks its whole slab against three oracle vectors."""
+    from oracle import c_oracle as co
+    out = {}
+    ns = 128 if world <= 4 else 256  # P/W and Q/W must be powers of two >= 16 for the peer-mapped form
+    ls = ns.bit_length() - 1
+    g = torch.Generator(device="cuda")
+    g.manual_seed(1234)
+    full = torch.randn(ns, ns, ns, dtype=torch.float64, device="cuda", generator=g)  # same on every rank
+    slab = make_slab(ns)
+    mine = full[rank * (ns // world):(rank + 1) * (ns // world)].contiguous()
+    f = slab.forward(mine, ns, ls, ls, ls).clone()
+    r = slab.reverse(f, ns, ls, ls, ls).clone()
+    parts_f = [torch.empty_like(f) for _ in range(world)]
+    parts_r = [torch.empty_like(r) for _ in range(world)]
+    dist.all_gather(parts_f, f)
+    dist.all_gather(parts_r, r)
+    if rank == 0:
+        xf = full.cpu().numpy()
+        want_f = co.transform_3d(co.FWT, co.FORWARD, cls, xf, ls, ls, ls)
+        got_f = torch.cat(parts_f).cpu().numpy()
+        want_r = co.transform_3d(co.FWT, co.REVERSE, cls, got_f, ls, ls, ls)
+        out["small_volume"] = f"{ns}^3"
+        out["small_forward_max_err"] = float(np.abs(got_f - want_f).max())
+        out["small_reverse_max_err"] = float(np.abs(torch.cat(parts_r).cpu().numpy() - want_r).max())
+        out["small_tol"] = 1e-12 * float(max(np.abs(xf).max(), np.abs(got_f).max()))
+    del slab, full, mine, f, r, parts_f, parts_r
+    # (b) separable probe at full size
+    rng = np.random.default_rng(77)
+    u, v, w = (rng.standard_normal(n) for _ in range(3))
+    fu, fv, fw = (co.transform_1d(co.FWT, co.FORWARD, cls, t, level) for t in (u, v, w))
+    tu, tv, tw, tfu, tfv, tfw = (torch.from_numpy(t).cuda() for t in (u, v, w, fu, fv, fw))
+    p = n // world
+    sl = slice(rank * p, (rank + 1) * p)
+    x = (tu[sl, None, None] * tv[None, :, None]) * tw[None, None, :]
+    slab = make_slab(n)
+    f = slab.forward(x.contiguous(), n, level, level, level)
+    want = (tfu[sl, None, None] * tfv[None, :, None]) * tfw[None, None, :]
+    e_f = (f - want).abs().max()
+    del want
+    back = slab.reverse(f.clone(), n, level, level, level)
+    e_r = (back - x).abs().max()
+    t = torch.stack([e_f, e_r, x.abs().max()])
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out["full_probe"] = f"{n}^3 rank-one volume u(x)v(x)w, every slab entry against the oracle's three 1-D transforms"
+    out["full_forward_max_err"] = float(t[0])
+    out["full_roundtrip_max_err"] = float(t[1])
+    out["full_tol"] = 1e-12 * float(t[2])
+    out["full_roundtrip_note"] = "Coiflet5's tap table reconstructs to ~5e-8 on the reference CPU too (SURVEY F8)"
+    del slab, x, f, back
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_workload(name, args, env):
+    """Device-resident timing, per-kernel roofline, e2e through the C ABI and the CPU sample of one workload."""
+    torch, dist, np, jw, _lib = env["torch"], env["dist"], env["np"], env["jw"], env["_lib"]
+    from jwave_b200.device import DeviceTransforms
+    rank, world, local = env["rank"], env["world"], env["local"]
+    cls, kind, n, level, batch, desc = WORKLOADS[name]
     if args.batch:
         batch = args.batch
-    dims = {"fwt": 1, "wpt": 1, "fwt2d": 2, "fwt3d": 3}[kind]
+    dims = DIMS[kind]
     K = _lib.WPT if kind == "wpt" else _lib.FWT
     wavelet = jw.WaveletBuilder.create(cls)
     L = wavelet.getMotherWavelength()
     dev = DeviceTransforms(wavelet, local)
+    steps = args.steps if dims == 1 else max(3, min(args.steps, 5))  # the 2-D / 3-D steps are 50-150 ms each
+    warmup = max(args.warmup, 3) if dims == 1 else 3
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    slab, slab_mode, parity = None, None, None
+    shape = {1: (batch, n), 2: (batch, n, n), 3: (n, n, n)}[dims]
+    if dims == 3 and world > 1:
+        # config 5 proper: ONE volume, slab-decomposed along i, re-cut along j for the i pass
+        from jwave_b200.distributed import PeerSlabVolumeTransform, SlabVolumeTransform, device_axis_fn
+
+        def make_slab(edge):
+            if args.slab in ("peer", "copies"):
+                try:
+                    return PeerSlabVolumeTransform(dev, edge, edge, edge,
+                                                   exchange="stores" if args.slab == "peer" else "copies")
+                except Exception as e:  # no symmetric memory / shape not covered: NCCL path
+                    if rank == 0:
+                        print(f"[bench] peer-mapped slabs unavailable ({e}); using the all-to-all path", file=sys.stderr)
+            return SlabVolumeTransform(device_axis_fn(dev), kind=K)
+        parity = slab_parity(torch, dist, np, jw, _lib, make_slab, dev, cls, n, level, rank, world)
+        slab = make_slab(n)
+        slab_mode = {"PeerSlabVolumeTransform": "peer " + getattr(slab, "exchange", ""),
+                     "SlabVolumeTransform": "all-to-all"}[type(slab).__name__]
+        shape = (n // world, n, n)
 
     gen = torch.Generator(device="cuda")
     gen.manual_seed(42 + rank)
-    slab = None
-    shape = {1: (batch, n), 2: (batch, n, n), 3: (n, n, n)}[dims]
-    if dims == 3 and world > 1:
-        # config 5 proper: ONE volume, slab-decomposed along i, all-to-all for the i pass
-        from jwave_b200.distributed import PeerSlabVolumeTransform, SlabVolumeTransform, device_axis_fn
-        slab_mode = "all-to-all"
-        if args.slab in ("peer", "copies") and K == _lib.FWT:
-            try:  # peer-mapped slabs: exchanges folded into the kernels' stores, or strided device copies
-                slab = PeerSlabVolumeTransform(dev, n, n, n, exchange="stores" if args.slab == "peer" else "copies")
-                slab_mode = "peer stores" if args.slab == "peer" else "peer copies"
-            except Exception as e:  # no symmetric memory / shape not covered: NCCL path
-                print(f"[bench] peer-mapped slabs unavailable ({e}); using the all-to-all path", file=sys.stderr)
-        if slab is None:
-            slab = SlabVolumeTransform(device_axis_fn(dev), kind=K)
-        shape = (n // world, n, n)
-    x = torch.randn(*shape, dtype=torch.float64, device="cuda", generator=gen)
-    coef = torch.empty_like(x)
-    back = torch.empty_like(x)
+    if dims == 2:
+        # 64 images = 32 GiB per array: the reverse writes back into `x` (x -> coef -> x), three full-size arrays
+        # (x, coef, the library's axis scratch) instead of four; image 0 is kept aside for the round-trip check
+        x = torch.empty(*shape, dtype=torch.float64, device="cuda")
+        for i in range(shape[0]):
+            x[i].normal_(generator=gen)
+        x0 = x[0].clone()
+        coef = torch.empty_like(x)
+        back = x
+    else:
+        x = torch.randn(*shape, dtype=torch.float64, device="cuda", generator=gen)
+        coef = torch.empty_like(x)
+        back = torch.empty_like(x)
 
     def run(direction, src, dst):
         if slab is not None:
@@ -313,30 +470,23 @@ def main():
             dev.transform3d(K, direction, src, level, level, level, out=dst)
         return dst
 
-    def step():
-        return run(_lib.REVERSE, run(_lib.FORWARD, x, coef), back)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        back = step()
+    res = None
+    for _ in range(warmup):
+        res = run(_lib.REVERSE, run(_lib.FORWARD, x, coef), back)
     barrier()
-    rt_err = float((back - x).abs().max())  # sanity: the timed work really is a transform pair
+    rt_err = float((res[0] - x0).abs().max()) if dims == 2 else float((res - x).abs().max())
 
-    # ---- timed region: K steps, device resident ------------------------------------------------
+    # ---- timed region: `steps` steps, device resident ------------------------------------------------
     sampler = ClockSampler(local, getattr(torch.cuda.get_device_properties(local), "uuid", None)) if rank == 0 else None
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    fwd_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    fwd_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     launches0 = dev.launch_count()
     if sampler:
         sampler.start()
     dev.ctx.profile(True)  # event pair around every kernel launch, read after the timed region
     barrier()
     ev[0].record()
-    for i in range(args.steps):
+    for i in range(steps):
         fwd_ev[i][0].record()
         c = run(_lib.FORWARD, x, coef)
         fwd_ev[i][1].record()
@@ -353,27 +503,26 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, fwd_ms = float(t[0]), float(t[1])
-    ms_per_step = ms / args.steps
+    ms_per_step = ms / steps
     rev_ms = ms_per_step - fwd_ms
     samples = x.numel()  # per GPU
     value = 2.0 * samples * world / (ms_per_step * 1e-3) * 1e-9
 
     # ---- roofline of the dominant kernel ------------------------------------------------------------
-    # Per-kernel CUDA-event times from the timed region (jwc_profile_*).  Algorithmic work of one
-    # launch: 16 B per sample it transforms (one read + one write), and
-    # direct-form flops 4 L (1 - 2^-m) per sample for m fused FWT levels, 2 L m for m WPT levels.
+    # Per-kernel CUDA-event times from the timed region (jwc_profile_*).  Algorithmic work of one launch
+    # (SURVEY.md section 8d): 16 B per sample it transforms (one read + one write), and direct-form flops
+    # 4 L (1 - 2^-m) per sample for m fused FWT levels, 2 L m for m WPT levels.
     hbm_peak, peak_src = peaks()
     bytes_per_sample = 16.0 * dims
     flops_per_sample = 2.0 * L * level if kind == "wpt" else dims * (2.0 * L * 2.0 * (1.0 - 0.5 ** level))
     prof_total = sum(r[2] for r in prof) or 1.0
     kernels = []
-    for name, count, total_ms, units, lv in prof:
-        t = total_ms / count * 1e-3
-        k_bytes = 16.0 * units
-        k_flops = units * (2.0 * L * lv if "wpt" in name else 4.0 * L * (1.0 - 0.5 ** lv))
-        kernels.append({"kernel": f"{name}<{L}>", "launches": count, "avg_ms": total_ms / count,
+    for kname, count, total_ms, units, lv in prof:
+        tk = total_ms / count * 1e-3
+        k_flops = units * (2.0 * L * lv if "wpt" in kname else 4.0 * L * (1.0 - 0.5 ** lv))
+        kernels.append({"kernel": f"{kname}<{L}>", "launches": count, "avg_ms": total_ms / count,
                         "share": total_ms / prof_total, "samples_per_launch": units, "levels": lv,
-                        "hbm_frac": k_bytes / t * 1e-9 / hbm_peak, "fp64_frac": k_flops / t * 1e-12 / FP64_PEAK_TFLOPS})
+                        "hbm_frac": 16.0 * units / tk * 1e-9 / hbm_peak, "fp64_frac": k_flops / tk * 1e-12 / FP64_PEAK_TFLOPS})
     kernels.sort(key=lambda k: -k["share"])
     dom = kernels[0]
     t_dom = dom["avg_ms"] * 1e-3
@@ -388,7 +537,7 @@ def main():
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from ncu --set full captures
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(f"{args.workload}:{dom['kernel']}")
+        traffic = json.load(open(tpath)).get(f"{name}:{dom['kernel']}")
     t_hbm = samples * bytes_per_sample / (hbm_peak * 1e9)
     t_fp64 = samples * flops_per_sample / (FP64_PEAK_TFLOPS * 1e12)
     t_roof = max(t_hbm, t_fp64)
@@ -396,29 +545,56 @@ def main():
                  "kernel_avg_ms": dom["avg_ms"], "kernels": kernels,
                  "forward_ms": fwd_ms, "reverse_ms": rev_ms,
                  "algorithmic_bytes_per_sample": bytes_per_sample, "algorithmic_flops_per_sample": flops_per_sample,
-                 "direction_roofline": "hbm" if t_hbm >= t_fp64 else "fp64",
-                 "forward_frac": t_roof / (fwd_ms * 1e-3), "reverse_frac": t_roof / (rev_ms * 1e-3)})
+                 "direction_roofline": "hbm" if t_hbm >= t_fp64 else "fp64"})
+    if slab is None:  # per-GPU roofline fractions of a whole direction (a slab step also holds the exchanges)
+        roof.update({"forward_frac": t_roof / (fwd_ms * 1e-3), "reverse_frac": t_roof / (rev_ms * 1e-3)})
+    slab_info = None
+    if slab is not None:
+        xb = slab.exchange_bytes(x) if hasattr(slab, "exchange_bytes") else x.numel() * 8 * (world - 1) // world
+        slab_info = {"mode": slab_mode, "exchanges_per_direction": 2, "bytes_sent_per_gpu_per_exchange": xb,
+                     "local_compute_roofline_ms_per_step": 2.0 * t_roof * 1e3,
+                     "note": "value is strong-scaled: one 1024^3 volume over all GPUs"}
+        if hasattr(slab, "measure"):
+            mm = slab.measure(x, level)  # one forward call: as run / local passes only / copies only
+            if mm:
+                tm = torch.tensor([mm["full_ms"], mm["compute_only_ms"], mm["copies_only_ms"]], dtype=torch.float64, device="cuda")
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+                slab_info.update({"forward_ms_as_run": float(tm[0]), "forward_ms_local_passes_only": float(tm[1]),
+                                  "forward_ms_copies_only": float(tm[2]), "chunks_per_exchange": slab.chunks,
+                                  "exposed_exchange_ms_per_direction": float(tm[0] - tm[1]),
+                                  "nvlink_gbs_sent_per_gpu_copies_alone": 2.0 * xb / (float(tm[2]) * 1e-3) * 1e-9})
 
-    # ---- e2e: the same step through the host-buffer C ABI ------------------------------------
+    del coef, back
+    if dims == 2:
+        del x0
+    # ---- e2e: the same step through the host-buffer C ABI, weak-scaled like `value` ----------------------
     e2e = None
-    if not args.no_e2e and dims == 1:
-        eb = batch if world == 1 else max(batch // world, 1)
-        host = jw.CudaFastWaveletTransform(wavelet, context=dev.ctx) if kind == "fwt" else \
-            jw.CudaWaveletPacketTransform(wavelet, context=dev.ctx)
-        hx = torch.empty(eb, n, dtype=torch.float64).pin_memory()
+    if not args.no_e2e and slab is None:
+        item = {1: n, 2: n * n, 3: n * n * n}[dims]
+        want = {1: batch, 2: min(batch, 8), 3: 1}[dims]  # 2-D: 8 images (4 GiB per host array) stand for the 64
+        eb = host_fit(want, item * 8, env["ranks_per_node"])
+        lib, hnd, wid = dev.ctx._lib, dev.ctx.handle, dev.wid
+        hx = torch.empty(eb * item, dtype=torch.float64).pin_memory()
         hc = torch.empty_like(hx).pin_memory()
         hb = torch.empty_like(hx).pin_memory()
-        hx.copy_(x[:eb])
-        f1d = dev.ctx._lib.jwc_fwt1d if kind == "fwt" else dev.ctx._lib.jwc_wpt1d
+        hx.copy_(x.reshape(-1)[:eb * item])
+
+        def call(direction, src, dst):
+            if dims == 1:
+                fn = lib.jwc_fwt1d if kind == "fwt" else lib.jwc_wpt1d
+                st = fn(hnd, wid, direction, src.data_ptr(), dst.data_ptr(), eb, n, level)
+            elif dims == 2:
+                st = lib.jwc_fwt2d(hnd, wid, direction, src.data_ptr(), dst.data_ptr(), eb, n, n, level, level)
+            else:
+                st = lib.jwc_fwt3d(hnd, wid, direction, src.data_ptr(), dst.data_ptr(), n, n, n, level, level, level)
+            dev.ctx.check(st, "e2e")
 
         def e2e_step():
-            st = f1d(dev.ctx.handle, dev.wid, _lib.FORWARD, hx.data_ptr(), hc.data_ptr(), eb, n, level)
-            dev.ctx.check(st, "e2e forward")
-            st = f1d(dev.ctx.handle, dev.wid, _lib.REVERSE, hc.data_ptr(), hb.data_ptr(), eb, n, level)
-            dev.ctx.check(st, "e2e reverse")
+            call(_lib.FORWARD, hx, hc)
+            call(_lib.REVERSE, hc, hb)
 
         e2e_step()
-        e2e_steps = max(2, min(args.steps, 5))
+        e2e_steps = max(2, min(args.steps, 3 if dims > 1 else 5))
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
@@ -427,37 +603,107 @@ def main():
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        nbytes = eb * n * 8
-        e2e = {"value": 2.0 * eb * n * world * e2e_steps / float(dt[0]) * 1e-9, "unit": "GSamples/s",
+        nbytes = eb * item * 8
+        step_s = float(dt[0]) / e2e_steps
+        e2e = {"value": 2.0 * eb * item * world / step_s * 1e-9, "unit": "GSamples/s",
                "h2d_bytes_per_step": 2 * nbytes, "d2h_bytes_per_step": 2 * nbytes,
-               "signals_per_gpu": eb, "steps": e2e_steps,
+               "items_per_gpu": eb, "stated_items_per_gpu": batch, "steps": e2e_steps, "scaling": "weak",
                "roundtrip_max_abs_err": float((hb - hx).abs().max()),
-               "api": "jwc_fwt1d / jwc_wpt1d (host buffers, pinned; chunked H2D/compute/D2H pipeline)"}
+               "api": {1: "jwc_fwt1d / jwc_wpt1d", 2: "jwc_fwt2d", 3: "jwc_fwt3d"}[dims] +
+                      " (host buffers, pinned; chunked H2D / compute / D2H pipeline)"}
         del hx, hc, hb
+        if env.get("pcie_gbs") is None:
+            env["pcie_gbs"] = pcie_probe(torch, dist, world)
+        # both directions of the bus carry 2 * nbytes per step; the probe keeps both busy at once
+        e2e["pcie"] = {"gbs_per_direction_per_gpu_concurrent": env["pcie_gbs"],
+                       "achieved_gbs_per_direction_per_gpu": 2 * nbytes / step_s * 1e-9,
+                       "how": "1 GiB pinned H2D and D2H copies in flight together on every rank at once"}
+        e2e["frac_of_pcie_ceiling"] = e2e["pcie"]["achieved_gbs_per_direction_per_gpu"] / env["pcie_gbs"]
+    del x
+    dev.close()
+    torch.cuda.empty_cache()
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu and dims == 1:
+    if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_sample(cls, kind, n, level)
 
+    rec = {
+        "value": value, "unit": "GSamples/s", "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step,
+        "scaling": "strong" if slab is not None else "weak",
+        "config": {"workload": desc + (f"; slab-decomposed over {world} GPUs ({slab_mode})" if slab is not None else ""),
+                   "step": "forward + reverse of the whole batch",
+                   "items_per_gpu": batch, "shape": list(shape), "n": n, "level": level, "wavelet": cls, "taps": L,
+                   "parallelism": (f"one volume in i-slabs over {world} GPUs, two re-cuts per direction" if slab is not None
+                                   else f"signals sharded over {world} GPU(s), no collective"),
+                   "l2": f"inputs ({samples * 8 / 2**30:.1f} GiB per array) exceed the 126 MB L2; no flush needed"},
+        "forward_gsps": samples * world / (fwd_ms * 1e-3) * 1e-9,
+        "reverse_gsps": samples * world / (rev_ms * 1e-3) * 1e-9,
+        "roundtrip_max_abs_err": rt_err,
+        "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+    }
+    if slab_info:
+        rec["slab"] = slab_info
+    if parity:
+        rec["slab_parity"] = parity
+        rec["slab_parity_max_err"] = max(parity.get("small_forward_max_err", 0.0), parity.get("small_reverse_max_err", 0.0),
+                                         parity["full_forward_max_err"])
+    return rec
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", choices=["all"] + sorted(WORKLOADS), default="all")
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--batch", type=int, default=0, help="override items per GPU (debug only)")
+    ap.add_argument("--slab", choices=["peer", "copies", "all2all"], default="copies",
+                    help="c5 on N > 1 GPUs: peer-mapped slabs filled by chunked device copies (default) or by the "
+                         "axis kernels' own stores (peer), or NCCL all-to-all")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import jwave_b200 as jw
+    from jwave_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    env = {"torch": torch, "dist": dist, "np": np, "jw": jw, "_lib": _lib, "rank": rank, "world": world, "local": local,
+           "ranks_per_node": int(os.environ.get("LOCAL_WORLD_SIZE", world)), "pcie_gbs": None}
+
+    names = ["c2", "c3", "c4", "c5"] if args.workload == "all" else [args.workload]
+    recs = {}
+    for nm in names:
+        try:
+            recs[nm] = run_workload(nm, args, env)
+        except Exception as e:  # a failing side workload must not take the headline down with it
+            if nm == names[0]:
+                raise
+            recs[nm] = {"error": f"{type(e).__name__}: {e}"}
+            torch.cuda.empty_cache()
     if rank == 0:
-        line = {
-            "metric": METRIC, "value": value, "unit": "GSamples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "strong" if slab is not None else "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc + (f"; one volume slab-decomposed over {world} GPUs, "
-                                           + {"peer stores": "exchanges folded into the axis kernels' peer stores",
-                                              "peer copies": "blocks copied straight into the peers' slabs (no pack / unpack / NCCL)",
-                                              "all-to-all": "2 all-to-all per direction"}[slab_mode]
-                                           if slab is not None else ""), "step": "forward + reverse of the whole batch",
-                       "items_per_gpu": batch, "shape": list(shape), "n": n, "level": level, "wavelet": cls, "taps": L,
-                       "parallelism": f"signals sharded over {world} GPU(s), no collective",
-                       "l2": f"inputs ({samples * 8 / 2**30:.1f} GiB per array) exceed the 126 MB L2; no flush needed"},
-            "forward_gsps": samples * world / (fwd_ms * 1e-3) * 1e-9,
-            "reverse_gsps": samples * world / (rev_ms * 1e-3) * 1e-9,
-            "roundtrip_max_abs_err": rt_err,
-            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-        }
+        head = recs[names[0]]
+        line = {"metric": METRIC, "value": head["value"], "unit": "GSamples/s", "n_gpus": world,
+                "steps": head["steps"], "warmup": head["warmup"], "ms_per_step": head["ms_per_step"],
+                "higher_is_better": True, "scaling": head["scaling"], "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic"}
+        line.update({k: v for k, v in head.items() if k not in line})
+        if len(names) > 1:
+            line["workloads"] = {nm: recs[nm] for nm in names[1:]}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

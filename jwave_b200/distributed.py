@@ -115,7 +115,7 @@ class PeerSlabVolumeTransform:
     stays valid until the next-but-one call.  FWT only (the WPT has no fused strided kernels), P/W and
     Q/W powers of two, R a multiple of 8; use SlabVolumeTransform otherwise."""
 
-    def __init__(self, dev, P, Q, R, group=None, exchange="stores"):
+    def __init__(self, dev, P, Q, R, group=None, exchange="stores", chunks=None):
         """exchange = "stores": the axis kernels store into the peers (fewest passes over the data, but a
         strided-axis CTA owns 64-byte pieces of each row - fine for 2 peers, slow across 8);
         "copies": the passes stay local and W - 1 strided device copies per exchange write the blocks
@@ -144,6 +144,13 @@ class PeerSlabVolumeTransform:
             self._peer = getattr(self, "_peer", {})
             self._peer[key] = [h.get_buffer(r, (numel,), torch.float64) for r in range(W)]
             self._ptrs[key] = [t_.data_ptr() for t_ in self._peer[key]]
+        # "copies": chunks per re-cut (JWB_SLAB_CHUNKS overrides); each chunk keeps whole 16-column blocks
+        import os
+        C = int(os.environ.get("JWB_SLAB_CHUNKS", chunks or 4))
+        while C > 1 and (self.p % C or self.q % C or (self.q // C) * R % 16):
+            C //= 2
+        self.chunks = max(C, 1)
+        self._copy_stream = torch.cuda.Stream(device=device)
         self._tmp = torch.empty(self.p * Q * R, dtype=torch.float64, device=device)
         self._tmp2 = torch.empty(self.p * Q * R, dtype=torch.float64, device=device) if exchange == "copies" else None
         self._flip = 0
@@ -177,30 +184,79 @@ class PeerSlabVolumeTransform:
         self._hdl[key].barrier()   # ... and in my i-slab
         return self._bufs[key].view(p, Q, R)
 
-    def _run_copies(self, direction, slab, lvlP, lvlQ, lvlR, key):
-        p, q, P, Q, R, rank, W = self.p, self.q, self.P, self.Q, self.R, self.rank, self.world
+    def _run_copies(self, direction, slab, lvlP, lvlQ, lvlR, key, compute=True, copies=True):
+        """Chunked, overlapped form.  Phase A: the owned slices are cut into C chunks; chunk c runs its two local
+        passes (k and j) on the compute stream while the copy stream writes chunk c - 1 straight into the peers'
+        j-slabs.  Phase B: the j-slab is held as C dense sub-slabs [P][q/C][R]; sub-slab c runs the i pass while
+        the copy stream writes sub-slab c - 1 into the peers' i-slabs in their final layout.  Only the last
+        chunk of each re-cut is exposed.  `compute` / `copies` switch either half off (measure())."""
+        p, q, P, Q, R, rank, W, C = self.p, self.q, self.P, self.Q, self.R, self.rank, self.world, self.chunks
         dev, J = self.dev, self._bufs["J"]
+        comp, cs = torch.cuda.current_stream(dev.device), self._copy_stream
         a, b = self._tmp.view(p, Q, R), self._tmp2.view(p, Q, R)
-        if direction == FORWARD:
-            dev.axis(FWT, FORWARD, slab, p * Q, R, 1, lvlQ, out=a)
-            dev.axis(FWT, FORWARD, a, p, Q, R, lvlP, out=b)
-        else:
-            dev.axis(FWT, REVERSE, slab, p, Q, R, lvlP, out=a)
-            dev.axis(FWT, REVERSE, a, p * Q, R, 1, lvlQ, out=b)
-        self._hdl["J"].barrier()
-        src = b.view(p, W, q, R)
-        for k in range(W):  # start with my own block, then round the ring so the peers are hit evenly
-            d = (rank + k) % W
-            self._peer["J"][d].view(P, q, R)[rank * p:(rank + 1) * p].copy_(src[:, d])
-        self._hdl["J"].barrier()
-        y = self._tmp.view(P, q, R)
-        dev.axis(FWT, direction, J.view(P, q, R), 1, P, q * R, lvlR, out=y)
-        self._hdl[key].barrier()
-        for k in range(W):
-            d = (rank + k) % W
-            self._peer[key][d].view(p, W, q, R)[:, rank].copy_(y.view(W, p, q, R)[d])
+        S, qc = p // C, q // C
+        Jc = J.view(C, P, qc, R)                      # my j-slab as C dense sub-slabs
+        peerJ = [t.view(C, P, qc, R) for t in self._peer["J"]]
+        peerI = [t.view(p, W, C, qc, R) for t in self._peer[key]]
+        y = self._tmp.view(C, P, qc, R)               # phase B output (phase A's `a` is dead by then)
+        # No barrier on entry: every rank passed the closing barrier of the previous call only after its own i
+        # passes had read its j-slab, and after phase A of that call had read the i-slab it was given.
+        for c in range(C):
+            sl = slice(c * S, (c + 1) * S)
+            if compute:
+                if direction == FORWARD:   # BasicTransform.java:509-566 (F5): k gets lvlQ, j gets lvlP
+                    dev.axis(FWT, FORWARD, slab[sl], S * Q, R, 1, lvlQ, out=a[sl])
+                    dev.axis(FWT, FORWARD, a[sl], S, Q, R, lvlP, out=b[sl])
+                else:                      # BasicTransform.java:602-659: columns, then rows
+                    dev.axis(FWT, REVERSE, slab[sl], S, Q, R, lvlP, out=a[sl])
+                    dev.axis(FWT, REVERSE, a[sl], S * Q, R, 1, lvlQ, out=b[sl])
+            if copies:
+                ev = torch.cuda.Event()
+                ev.record(comp)
+                with torch.cuda.stream(cs):
+                    cs.wait_event(ev)
+                    src = b[sl].view(S, W, C, qc, R)
+                    for k in range(W):  # start with my own block, then round the ring so the peers are hit evenly
+                        d = (rank + k) % W
+                        peerJ[d][:, rank * p + c * S:rank * p + (c + 1) * S].copy_(src[:, d].permute(1, 0, 2, 3))
+        comp.wait_stream(cs)
+        self._hdl["J"].barrier()                      # every rank's rows have landed in my j-slab
+        for c in range(C):
+            if compute:
+                dev.axis(FWT, direction, Jc[c], 1, P, qc * R, lvlR, out=y[c])
+            if copies:
+                ev = torch.cuda.Event()
+                ev.record(comp)
+                with torch.cuda.stream(cs):
+                    cs.wait_event(ev)
+                    for k in range(W):
+                        d = (rank + k) % W
+                        peerI[d][:, rank, c].copy_(y[c].view(W, p, qc, R)[d])
+        comp.wait_stream(cs)
         self._hdl[key].barrier()
         return self._bufs[key].view(p, Q, R)
+
+    def exchange_bytes(self, slab=None):
+        """Bytes this rank sends to OTHER GPUs per re-cut (the NVLink term of the step)."""
+        return self.p * self.Q * self.R * 8 * (self.world - 1) // self.world
+
+    def measure(self, slab, lvl, reps=3):
+        """Device time (ms, max over ranks is the caller's business) of one forward call as run, with the local
+        passes only and with the copies only - what the re-cuts cost alone and how much of that the overlap hides."""
+        if self.exchange != "copies":
+            return {}
+        out = {}
+        for tag, kw in (("full", {}), ("compute_only", {"copies": False}), ("copies_only", {"compute": False})):
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            self._run_copies(FORWARD, slab, lvl, lvl, lvl, "I0", **kw)
+            torch.cuda.synchronize()
+            evs[0].record()
+            for i in range(reps):
+                self._run_copies(FORWARD, slab, lvl, lvl, lvl, "I%d" % (i & 1), **kw)
+            evs[1].record()
+            torch.cuda.synchronize()
+            out[tag + "_ms"] = evs[0].elapsed_time(evs[1]) / reps
+        return out
 
     def forward(self, slab, P, lvlP, lvlQ, lvlR, out=None):
         y = self._run(FORWARD, slab, lvlP, lvlQ, lvlR)
