@@ -340,7 +340,30 @@ def pcie_probe(torch, dist, world, nbytes=1 << 30, reps=4):
     return nbytes * reps / float(dt[0]) * 1e-9  # GB/s per direction per GPU, both directions busy
 
 
-def slab_parity(torch, dist, np, jw, _lib, make_slab, dev, cls, n, level, rank, world):
+class SlabRunner:
+    """forward / reverse of this rank's slab through one of the slab classes; layout "j" keeps the coefficients in
+    the j-slab layout between the two (one re-cut per direction), layout "i" returns them as i-slabs (two)."""
+
+    def __init__(self, slab, n, level, layout):
+        self.slab, self.n, self.level = slab, n, level
+        self.layout = layout if hasattr(slab, "forward_t") and getattr(slab, "exchange", "") == "copies" else "i"
+
+    def forward(self, x, out=None):
+        if self.layout == "j":
+            return self.slab.forward_t(x, self.n, self.level, self.level, self.level)
+        return self.slab.forward(x, self.n, self.level, self.level, self.level, out=out)
+
+    def reverse(self, c, out=None):
+        if self.layout == "j":
+            return self.slab.reverse_t(c, self.n, self.level, self.level, self.level)
+        return self.slab.reverse(c, self.n, self.level, self.level, self.level, out=out)
+
+    def dense_coef(self, c):
+        """(dense slab of coefficients, the axis the ranks' slabs are concatenated along)"""
+        return (self.slab.t_to_dense(c), 1) if self.layout == "j" else (c, 0)
+
+
+def slab_parity(torch, dist, np, make_runner, cls, n, level, rank, world):
     """c5 at N > 1: parity of the slab-decomposed path against the oracle, visible in the bench line because the
     driver's test box has one GPU.  (a) a small random volume through the same slab code, gathered and compared
     with the oracle's 3-D transform; (b) the FULL 1024^3 volume with a separable probe x = u (x) v (x) w: the
@@ -353,10 +376,12 @@ def slab_parity(torch, dist, np, jw, _lib, make_slab, dev, cls, n, level, rank, 
     g = torch.Generator(device="cuda")
     g.manual_seed(1234)
     full = torch.randn(ns, ns, ns, dtype=torch.float64, device="cuda", generator=g)  # same on every rank
-    slab = make_slab(ns)
+    run = make_runner(ns, ls)
     mine = full[rank * (ns // world):(rank + 1) * (ns // world)].contiguous()
-    f = slab.forward(mine, ns, ls, ls, ls).clone()
-    r = slab.reverse(f, ns, ls, ls, ls).clone()
+    fc = run.forward(mine)
+    f, axis = run.dense_coef(fc)
+    f = f.clone()
+    r = run.reverse(fc).clone()
     parts_f = [torch.empty_like(f) for _ in range(world)]
     parts_r = [torch.empty_like(r) for _ in range(world)]
     dist.all_gather(parts_f, f)
@@ -364,13 +389,13 @@ def slab_parity(torch, dist, np, jw, _lib, make_slab, dev, cls, n, level, rank, 
     if rank == 0:
         xf = full.cpu().numpy()
         want_f = co.transform_3d(co.FWT, co.FORWARD, cls, xf, ls, ls, ls)
-        got_f = torch.cat(parts_f).cpu().numpy()
+        got_f = torch.cat(parts_f, dim=axis).cpu().numpy()
         want_r = co.transform_3d(co.FWT, co.REVERSE, cls, got_f, ls, ls, ls)
         out["small_volume"] = f"{ns}^3"
         out["small_forward_max_err"] = float(np.abs(got_f - want_f).max())
         out["small_reverse_max_err"] = float(np.abs(torch.cat(parts_r).cpu().numpy() - want_r).max())
         out["small_tol"] = 1e-12 * float(max(np.abs(xf).max(), np.abs(got_f).max()))
-    del slab, full, mine, f, r, parts_f, parts_r
+    del run, full, mine, f, fc, r, parts_f, parts_r
     # (b) separable probe at full size
     rng = np.random.default_rng(77)
     u, v, w = (rng.standard_normal(n) for _ in range(3))
@@ -378,13 +403,17 @@ def slab_parity(torch, dist, np, jw, _lib, make_slab, dev, cls, n, level, rank, 
     tu, tv, tw, tfu, tfv, tfw = (torch.from_numpy(t).cuda() for t in (u, v, w, fu, fv, fw))
     p = n // world
     sl = slice(rank * p, (rank + 1) * p)
-    x = (tu[sl, None, None] * tv[None, :, None]) * tw[None, None, :]
-    slab = make_slab(n)
-    f = slab.forward(x.contiguous(), n, level, level, level)
-    want = (tfu[sl, None, None] * tfv[None, :, None]) * tfw[None, None, :]
+    x = ((tu[sl, None, None] * tv[None, :, None]) * tw[None, None, :]).contiguous()
+    run = make_runner(n, level)
+    fc = run.forward(x)
+    f, axis = run.dense_coef(fc)
+    if axis == 0:
+        want = (tfu[sl, None, None] * tfv[None, :, None]) * tfw[None, None, :]
+    else:
+        want = (tfu[:, None, None] * tfv[None, sl, None]) * tfw[None, None, :]
     e_f = (f - want).abs().max()
-    del want
-    back = slab.reverse(f.clone(), n, level, level, level)
+    del want, f
+    back = run.reverse(fc)
     e_r = (back - x).abs().max()
     t = torch.stack([e_f, e_r, x.abs().max()])
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -393,7 +422,8 @@ def slab_parity(torch, dist, np, jw, _lib, make_slab, dev, cls, n, level, rank, 
     out["full_roundtrip_max_err"] = float(t[1])
     out["full_tol"] = 1e-12 * float(t[2])
     out["full_roundtrip_note"] = "Coiflet5's tap table reconstructs to ~5e-8 on the reference CPU too (SURVEY F8)"
-    del slab, x, f, back
+    out["coefficient_layout"] = run.layout + "-slabs"
+    del run, x, fc, back
     torch.cuda.empty_cache()
     return out
 
@@ -434,10 +464,13 @@ def run_workload(name, args, env):
                     if rank == 0:
                         print(f"[bench] peer-mapped slabs unavailable ({e}); using the all-to-all path", file=sys.stderr)
             return SlabVolumeTransform(device_axis_fn(dev), kind=K)
-        parity = slab_parity(torch, dist, np, jw, _lib, make_slab, dev, cls, n, level, rank, world)
-        slab = make_slab(n)
-        slab_mode = {"PeerSlabVolumeTransform": "peer " + getattr(slab, "exchange", ""),
-                     "SlabVolumeTransform": "all-to-all"}[type(slab).__name__]
+
+        def make_runner(edge, lv):
+            return SlabRunner(make_slab(edge), edge, lv, args.slab_layout)
+        parity = slab_parity(torch, dist, np, make_runner, cls, n, level, rank, world)
+        slab = make_runner(n, level)
+        slab_mode = {"PeerSlabVolumeTransform": "peer " + getattr(slab.slab, "exchange", ""),
+                     "SlabVolumeTransform": "all-to-all"}[type(slab.slab).__name__] + f", coefficients in {slab.layout}-slabs"
         shape = (n // world, n, n)
 
     gen = torch.Generator(device="cuda")
@@ -458,10 +491,8 @@ def run_workload(name, args, env):
 
     def run(direction, src, dst):
         if slab is not None:
-            out = dst if slab_mode == "all-to-all" else None  # the peer paths return their own symmetric buffer
-            if direction == _lib.FORWARD:
-                return slab.forward(src, n, level, level, level, out=out)
-            return slab.reverse(src, n, level, level, level, out=out)
+            out = dst if slab_mode.startswith("all-to-all") else None  # the peer paths return their own buffers
+            return slab.forward(src, out=out) if direction == _lib.FORWARD else slab.reverse(src, out=out)
         elif dims == 1:
             dev.transform1d(K, direction, src, level, out=dst)
         elif dims == 2:
@@ -550,19 +581,20 @@ def run_workload(name, args, env):
         roof.update({"forward_frac": t_roof / (fwd_ms * 1e-3), "reverse_frac": t_roof / (rev_ms * 1e-3)})
     slab_info = None
     if slab is not None:
-        xb = slab.exchange_bytes(x) if hasattr(slab, "exchange_bytes") else x.numel() * 8 * (world - 1) // world
-        slab_info = {"mode": slab_mode, "exchanges_per_direction": 2, "bytes_sent_per_gpu_per_exchange": xb,
+        xb = x.numel() * 8 * (world - 1) // world
+        nx = 1 if slab.layout == "j" else 2
+        slab_info = {"mode": slab_mode, "exchanges_per_direction": nx, "bytes_sent_per_gpu_per_exchange": xb,
                      "local_compute_roofline_ms_per_step": 2.0 * t_roof * 1e3,
                      "note": "value is strong-scaled: one 1024^3 volume over all GPUs"}
-        if hasattr(slab, "measure"):
-            mm = slab.measure(x, level)  # one forward call: as run / local passes only / copies only
+        if hasattr(slab.slab, "measure"):
+            mm = slab.slab.measure(x, level, coef=slab.layout)  # one forward call: as run / local passes only / copies only
             if mm:
                 tm = torch.tensor([mm["full_ms"], mm["compute_only_ms"], mm["copies_only_ms"]], dtype=torch.float64, device="cuda")
                 dist.all_reduce(tm, op=dist.ReduceOp.MAX)
                 slab_info.update({"forward_ms_as_run": float(tm[0]), "forward_ms_local_passes_only": float(tm[1]),
-                                  "forward_ms_copies_only": float(tm[2]), "chunks_per_exchange": slab.chunks,
+                                  "forward_ms_copies_only": float(tm[2]), "chunks_per_exchange": slab.slab.chunks,
                                   "exposed_exchange_ms_per_direction": float(tm[0] - tm[1]),
-                                  "nvlink_gbs_sent_per_gpu_copies_alone": 2.0 * xb / (float(tm[2]) * 1e-3) * 1e-9})
+                                  "nvlink_gbs_sent_per_gpu_copies_alone": nx * xb / (float(tm[2]) * 1e-3) * 1e-9})
 
     del coef, back
     if dims == 2:
@@ -661,6 +693,9 @@ def main():
     ap.add_argument("--slab", choices=["peer", "copies", "all2all"], default="copies",
                     help="c5 on N > 1 GPUs: peer-mapped slabs filled by chunked device copies (default) or by the "
                          "axis kernels' own stores (peer), or NCCL all-to-all")
+    ap.add_argument("--slab-layout", choices=["j", "i"], default="j",
+                    help="c5 on N > 1 GPUs (copies): leave the coefficients in j-slabs between forward and reverse (one "
+                         "re-cut per direction, SURVEY.md 8e) or return them as i-slabs (two)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -184,13 +184,13 @@ int jwc_h2d(jwc_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes); /*
 int jwc_d2h(jwc_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes); /* async on the stream */
 int jwc_host_alloc_pinned(jwc_ctx* ctx, size_t bytes, void** hptr);
 int jwc_host_free_pinned(jwc_ctx* ctx, void* hptr);
-/* Peer mapping between the per-GPU processes of one box (CUDA IPC): export a handle for a
- * jwc_dev_alloc'd buffer, open another rank's handle (peer access is enabled lazily), close it.  The
- * slab-decomposed volume uses these so the axis kernels can store straight into the peers' slabs. */
-#define JWC_IPC_HANDLE_BYTES 64
-int jwc_ipc_export(jwc_ctx* ctx, void* dptr, unsigned char handle[JWC_IPC_HANDLE_BYTES]);
-int jwc_ipc_open(jwc_ctx* ctx, const unsigned char handle[JWC_IPC_HANDLE_BYTES], void** dptr);
-int jwc_ipc_close(jwc_ctx* ctx, void* dptr);
+/* Strided device-to-device copy on the copy engines (cudaMemcpy2DAsync): `height` rows of `width` bytes, source /
+ * destination pitches in bytes, enqueued on `cuda_stream` (a cudaStream_t; NULL = the context's current stream).
+ * Either pointer may be a mapping of a PEER GPU's memory (same process with peer access, or a cross-process
+ * mapping such as torch symmetric memory): this is what re-cuts a slab-decomposed volume over NVLink without
+ * taking SMs away from the axis passes that run beside it. */
+int jwc_copy2d_dev(jwc_ctx* ctx, void* dst, size_t dpitch, const void* src, size_t spitch, size_t width,
+                   size_t height, void* cuda_stream);
 /* Upper bound (bytes) for the staging chunk the host-buffer entry points move per step. */
 int jwc_set_staging_bytes(jwc_ctx* ctx, size_t bytes);
 

@@ -57,9 +57,7 @@ SIGNATURES = {
     "jwc_d2h": (_int, [_vp, _vp, _vp, C.c_size_t]),
     "jwc_host_alloc_pinned": (_int, [_vp, C.c_size_t, C.POINTER(_vp)]),
     "jwc_host_free_pinned": (_int, [_vp, _vp]),
-    "jwc_ipc_export": (_int, [_vp, _vp, C.POINTER(C.c_ubyte)]),
-    "jwc_ipc_open": (_int, [_vp, C.POINTER(C.c_ubyte), C.POINTER(_vp)]),
-    "jwc_ipc_close": (_int, [_vp, _vp]),
+    "jwc_copy2d_dev": (_int, [_vp, _vp, C.c_size_t, _vp, C.c_size_t, C.c_size_t, C.c_size_t, _vp]),
     "jwc_set_staging_bytes": (_int, [_vp, C.c_size_t]),
 }
 

@@ -813,27 +813,14 @@ extern "C" int jwc_host_free_pinned(jwc_ctx* ctx, void* hptr) {
   JWC_CUDA(ctx, cudaFreeHost(hptr));
   return JWC_OK;
 }
-extern "C" int jwc_ipc_export(jwc_ctx* ctx, void* dptr, unsigned char handle[JWC_IPC_HANDLE_BYTES]) {
-  if (!ctx || !dptr || !handle) return JWC_ERR_ARG;
-  static_assert(sizeof(cudaIpcMemHandle_t) == JWC_IPC_HANDLE_BYTES, "CUDA IPC handle size");
+extern "C" int jwc_copy2d_dev(jwc_ctx* ctx, void* dst, size_t dpitch, const void* src, size_t spitch, size_t width,
+                              size_t height, void* cuda_stream) {
+  if (!ctx || !dst || !src) return JWC_ERR_ARG;
+  if (width == 0 || height == 0) return JWC_OK;
+  if (dpitch < width || spitch < width) return fail(ctx, JWC_ERR_ARG, "jwc_copy2d_dev: pitch smaller than the row");
   JWC_CUDA(ctx, cudaSetDevice(ctx->device));
-  cudaIpcMemHandle_t h;
-  JWC_CUDA(ctx, cudaIpcGetMemHandle(&h, dptr));
-  memcpy(handle, &h, sizeof(h));
-  return JWC_OK;
-}
-extern "C" int jwc_ipc_open(jwc_ctx* ctx, const unsigned char handle[JWC_IPC_HANDLE_BYTES], void** dptr) {
-  if (!ctx || !dptr || !handle) return JWC_ERR_ARG;
-  JWC_CUDA(ctx, cudaSetDevice(ctx->device));
-  cudaIpcMemHandle_t h;
-  memcpy(&h, handle, sizeof(h));
-  JWC_CUDA(ctx, cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
-  return JWC_OK;
-}
-extern "C" int jwc_ipc_close(jwc_ctx* ctx, void* dptr) {
-  if (!ctx || !dptr) return JWC_ERR_ARG;
-  JWC_CUDA(ctx, cudaSetDevice(ctx->device));
-  JWC_CUDA(ctx, cudaIpcCloseMemHandle(dptr));
+  cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+  JWC_CUDA(ctx, cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyDefault, st));
   return JWC_OK;
 }
 

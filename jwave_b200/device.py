@@ -89,6 +89,13 @@ class DeviceTransforms:
         self.ctx.check(st, "jwc_3d_dev")
         return out
 
+    def copy2d(self, dst, dpitch, src, spitch, width, height, stream=None):
+        """jwc_copy2d_dev: strided device copy on the copy engines; dst / src are device pointers (ints), pitches
+        and width in bytes; `stream` a torch stream (default: the current one)."""
+        st = (stream or torch.cuda.current_stream(self.device)).cuda_stream
+        rc = self._L.jwc_copy2d_dev(self.ctx.handle, dst, dpitch, src, spitch, width, height, st)
+        self.ctx.check(rc, "jwc_copy2d_dev")
+
     def launch_count(self):
         return self.ctx.launch_count()
 

@@ -14,6 +14,8 @@ The local compute is injected (`axis_fn`), so the exchange logic is testable on 
 the `gloo` backend; on GPUs it is DeviceTransforms.axis (libjwave_cuda.so) and the collective
 runs over NCCL / NVLink.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -145,12 +147,14 @@ class PeerSlabVolumeTransform:
             self._peer[key] = [h.get_buffer(r, (numel,), torch.float64) for r in range(W)]
             self._ptrs[key] = [t_.data_ptr() for t_ in self._peer[key]]
         # "copies": chunks per re-cut (JWB_SLAB_CHUNKS overrides); each chunk keeps whole 16-column blocks
-        import os
         C = int(os.environ.get("JWB_SLAB_CHUNKS", chunks or 4))
         while C > 1 and (self.p % C or self.q % C or (self.q // C) * R % 16):
             C //= 2
         self.chunks = max(C, 1)
-        self._copy_stream = torch.cuda.Stream(device=device)
+        # several copy streams: one stream keeps one copy engine busy (~400 GB/s over NVLink measured), the re-cut
+        # of a chunk is W * C independent 2-D copies
+        ns = int(os.environ.get("JWB_SLAB_COPY_STREAMS", 4))
+        self._copy_streams = [torch.cuda.Stream(device=device, priority=-1) for _ in range(max(ns, 1))]
         self._tmp = torch.empty(self.p * Q * R, dtype=torch.float64, device=device)
         self._tmp2 = torch.empty(self.p * Q * R, dtype=torch.float64, device=device) if exchange == "copies" else None
         self._flip = 0
@@ -184,63 +188,130 @@ class PeerSlabVolumeTransform:
         self._hdl[key].barrier()   # ... and in my i-slab
         return self._bufs[key].view(p, Q, R)
 
-    def _run_copies(self, direction, slab, lvlP, lvlQ, lvlR, key, compute=True, copies=True):
-        """Chunked, overlapped form.  Phase A: the owned slices are cut into C chunks; chunk c runs its two local
-        passes (k and j) on the compute stream while the copy stream writes chunk c - 1 straight into the peers'
-        j-slabs.  Phase B: the j-slab is held as C dense sub-slabs [P][q/C][R]; sub-slab c runs the i pass while
-        the copy stream writes sub-slab c - 1 into the peers' i-slabs in their final layout.  Only the last
-        chunk of each re-cut is exposed.  `compute` / `copies` switch either half off (measure())."""
+    # ---- "copies": chunked re-cuts on the copy engines, overlapped with the local passes -------------------
+    # Layouts.  i-slab: [p][Q][R] (rank g owns i in [g p, (g+1) p)) - the layout BasicTransform returns, just
+    # distributed.  j-slab: my j range [g q, (g+1) q) for ALL i, held as C dense sub-slabs [C][P][q/C][R] so that
+    # every sub-slab is one dense [outer = 1][n = P][inner = q/C * R] problem for the i pass.
+    def _local_ij(self, direction, src, sl, lvlP, lvlQ):
+        """the two local passes (axes k and j) of the slices `sl` of an i-slab: src[sl] -> self._b[sl]"""
+        dev, Q, R = self.dev, self.Q, self.R
+        a, b = self._tmp.view(self.p, Q, R), self._tmp2.view(self.p, Q, R)
+        S = sl.stop - sl.start
+        if direction == FORWARD:   # BasicTransform.java:509-566 (F5): k gets lvlQ, j gets lvlP
+            dev.axis(FWT, FORWARD, src[sl], S * Q, R, 1, lvlQ, out=a[sl])
+            dev.axis(FWT, FORWARD, a[sl], S, Q, R, lvlP, out=b[sl])
+        else:                      # BasicTransform.java:602-659: columns, then rows
+            dev.axis(FWT, REVERSE, src[sl], S, Q, R, lvlP, out=a[sl])
+            dev.axis(FWT, REVERSE, a[sl], S * Q, R, 1, lvlQ, out=b[sl])
+
+    def _send_to_j(self, c, comp, cs):
+        """slices chunk c of my i-slab result (self._tmp2) -> the j-slabs of all ranks (DMA, copy stream)"""
         p, q, P, Q, R, rank, W, C = self.p, self.q, self.P, self.Q, self.R, self.rank, self.world, self.chunks
-        dev, J = self.dev, self._bufs["J"]
-        comp, cs = torch.cuda.current_stream(dev.device), self._copy_stream
-        a, b = self._tmp.view(p, Q, R), self._tmp2.view(p, Q, R)
         S, qc = p // C, q // C
-        Jc = J.view(C, P, qc, R)                      # my j-slab as C dense sub-slabs
-        peerJ = [t.view(C, P, qc, R) for t in self._peer["J"]]
-        peerI = [t.view(p, W, C, qc, R) for t in self._peer[key]]
-        y = self._tmp.view(C, P, qc, R)               # phase B output (phase A's `a` is dead by then)
+        ev = torch.cuda.Event()
+        ev.record(comp)
+        for st in cs:
+            st.wait_event(ev)
+        row = qc * R * 8                                   # one (slice, sub-slab) row: qc * R contiguous doubles
+        src0 = self._tmp2.data_ptr() + c * S * Q * R * 8   # b[c S][0][0]
+        n = 0
+        for k in range(W):  # start with my own block, then round the ring so the peers are hit evenly
+            d = (rank + k) % W
+            for cc in range(C):
+                # dst: J_d[cc][rank p + c S + s][:][:], s = 0 .. S - 1 (dense rows); src: b[c S + s][d q + cc qc][:]
+                dst = self._ptrs["J"][d] + ((cc * P + rank * p + c * S) * qc * R) * 8
+                src = src0 + ((d * q + cc * qc) * R) * 8
+                self.dev.copy2d(dst, row, src, Q * R * 8, row, S, stream=cs[n % len(cs)])
+                n += 1
+
+    def _send_to_i(self, c, key, comp, cs):
+        """sub-slab c of my j-slab result (self._y) -> the i-slabs `key` of all ranks, in their final layout"""
+        p, q, P, Q, R, rank, W, C = self.p, self.q, self.P, self.Q, self.R, self.rank, self.world, self.chunks
+        qc = q // C
+        ev = torch.cuda.Event()
+        ev.record(comp)
+        for st in cs:
+            st.wait_event(ev)
+        row = qc * R * 8
+        for k in range(W):
+            d = (rank + k) % W
+            # dst: I_d[i][rank q + c qc][:], i = 0 .. p - 1 (pitch Q R); src: y[c][d p + i][:][:] (dense rows)
+            dst = self._ptrs[key][d] + ((rank * q + c * qc) * R) * 8
+            src = self._y.data_ptr() + ((c * P + d * p) * qc * R) * 8
+            self.dev.copy2d(dst, Q * R * 8, src, row, row, p, stream=cs[(c * W + k) % len(cs)])
+
+    def _run_copies(self, direction, slab, lvlP, lvlQ, lvlR, key, compute=True, copies=True, coef="i"):
+        """direction FORWARD: i-slab in -> coefficients in the i-slab layout (coef="i", two re-cuts) or left in the
+        j-slab layout (coef="j", ONE re-cut).  REVERSE: coefficients in that layout -> i-slab of samples; with
+        coef="j" the i axis is rebuilt first - the order of ParallelTransform.reverse (ParallelTransform.java:193),
+        which differs from BasicTransform's by rounding only (the axis passes act on different indices).
+        Each re-cut is cut into C chunks whose copies run on the copy engines (copy stream) beside the next
+        chunk's axis passes; only the last chunk of a re-cut is exposed.  `compute` / `copies`: measure()."""
+        p, q, P, Q, R, C = self.p, self.q, self.P, self.Q, self.R, self.chunks
+        dev = self.dev
+        comp, cs = torch.cuda.current_stream(dev.device), self._copy_streams
+        S, qc = p // C, q // C
+        Jc = self._bufs["J"].view(C, P, qc, R)
+
+        def join_copies():
+            for st in cs:
+                comp.wait_stream(st)
         # No barrier on entry: every rank passed the closing barrier of the previous call only after its own i
-        # passes had read its j-slab, and after phase A of that call had read the i-slab it was given.
-        for c in range(C):
-            sl = slice(c * S, (c + 1) * S)
+        # passes had read its j-slab, and after the local passes of that call had read the i-slab it was given.
+        if direction == FORWARD or coef == "i":
+            for c in range(C):                           # re-cut 1: i-slabs -> j-slabs, behind the k / j passes
+                if compute:
+                    self._local_ij(direction, slab, slice(c * S, (c + 1) * S), lvlP, lvlQ)
+                if copies:
+                    self._send_to_j(c, comp, cs)
+            join_copies()
+            self._hdl["J"].barrier()                     # every rank's rows have landed in my j-slab
+            src_j = Jc
+        else:
+            src_j = slab                                 # coefficients already in the j-slab layout [C][P][qc][R]
+        last_recut = not (direction == FORWARD and coef == "j")
+        self._y = (self._tmp if (direction == FORWARD or coef == "i") else self._tmp2).view(C, P, qc, R)
+        for c in range(C):                               # the i pass, sub-slab by sub-slab
             if compute:
-                if direction == FORWARD:   # BasicTransform.java:509-566 (F5): k gets lvlQ, j gets lvlP
-                    dev.axis(FWT, FORWARD, slab[sl], S * Q, R, 1, lvlQ, out=a[sl])
-                    dev.axis(FWT, FORWARD, a[sl], S, Q, R, lvlP, out=b[sl])
-                else:                      # BasicTransform.java:602-659: columns, then rows
-                    dev.axis(FWT, REVERSE, slab[sl], S, Q, R, lvlP, out=a[sl])
-                    dev.axis(FWT, REVERSE, a[sl], S * Q, R, 1, lvlQ, out=b[sl])
-            if copies:
-                ev = torch.cuda.Event()
-                ev.record(comp)
-                with torch.cuda.stream(cs):
-                    cs.wait_event(ev)
-                    src = b[sl].view(S, W, C, qc, R)
-                    for k in range(W):  # start with my own block, then round the ring so the peers are hit evenly
-                        d = (rank + k) % W
-                        peerJ[d][:, rank * p + c * S:rank * p + (c + 1) * S].copy_(src[:, d].permute(1, 0, 2, 3))
-        comp.wait_stream(cs)
-        self._hdl["J"].barrier()                      # every rank's rows have landed in my j-slab
-        for c in range(C):
-            if compute:
-                dev.axis(FWT, direction, Jc[c], 1, P, qc * R, lvlR, out=y[c])
-            if copies:
-                ev = torch.cuda.Event()
-                ev.record(comp)
-                with torch.cuda.stream(cs):
-                    cs.wait_event(ev)
-                    for k in range(W):
-                        d = (rank + k) % W
-                        peerI[d][:, rank, c].copy_(y[c].view(W, p, qc, R)[d])
-        comp.wait_stream(cs)
+                dev.axis(FWT, direction, src_j[c], 1, P, qc * R, lvlR, out=self._y[c])
+            if copies and last_recut:                    # re-cut 2: j-slabs -> i-slabs
+                self._send_to_i(c, key, comp, cs)
+        if not last_recut:
+            self._hdl["J"].barrier()                     # closing barrier: my j-slab may be refilled by the next call
+            return self._y                               # forward, coef="j": [C][P][qc][R], no second re-cut
+        join_copies()
         self._hdl[key].barrier()
-        return self._bufs[key].view(p, Q, R)
+        out = self._bufs[key].view(p, Q, R)
+        if direction == REVERSE and coef == "j":         # the slices are rebuilt last, locally
+            if compute:
+                self._local_ij(REVERSE, out, slice(0, p), lvlP, lvlQ)
+            return self._tmp2.view(p, Q, R)
+        return out
+
+    def forward_t(self, slab, P, lvlP, lvlQ, lvlR):
+        """Forward transform that leaves the coefficients in the j-slab layout [C][P][q/C][R] (rank g owns
+        j in [g q, (g+1) q)): one re-cut instead of two.  `coef_to_i_slab_order` gives the
+        dense [P][q][R] copy of it.  The result lives in an internal buffer: valid until the next call."""
+        self._flip ^= 1
+        return self._run_copies(FORWARD, slab, lvlP, lvlQ, lvlR, "I%d" % self._flip, coef="j")
+
+    def reverse_t(self, coef_t, P, lvlP, lvlQ, lvlR):
+        """Reverse of forward_t: j-slab coefficients in, i-slab of samples out (internal buffer: valid until the
+        next call, which may take it as its input)."""
+        self._flip ^= 1
+        return self._run_copies(REVERSE, coef_t, lvlP, lvlQ, lvlR, "I%d" % self._flip, coef="j")
+
+    @staticmethod
+    def t_to_dense(coef_t):
+        """[C][P][q/C][R] -> the dense j-slab [P][q][R] (a copy)."""
+        C, P, qc, R = coef_t.shape
+        return coef_t.permute(1, 0, 2, 3).reshape(P, C * qc, R)
 
     def exchange_bytes(self, slab=None):
         """Bytes this rank sends to OTHER GPUs per re-cut (the NVLink term of the step)."""
         return self.p * self.Q * self.R * 8 * (self.world - 1) // self.world
 
-    def measure(self, slab, lvl, reps=3):
+    def measure(self, slab, lvl, reps=3, coef="i"):
         """Device time (ms, max over ranks is the caller's business) of one forward call as run, with the local
         passes only and with the copies only - what the re-cuts cost alone and how much of that the overlap hides."""
         if self.exchange != "copies":
@@ -248,11 +319,11 @@ class PeerSlabVolumeTransform:
         out = {}
         for tag, kw in (("full", {}), ("compute_only", {"copies": False}), ("copies_only", {"compute": False})):
             evs = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-            self._run_copies(FORWARD, slab, lvl, lvl, lvl, "I0", **kw)
+            self._run_copies(FORWARD, slab, lvl, lvl, lvl, "I0", coef=coef, **kw)
             torch.cuda.synchronize()
             evs[0].record()
             for i in range(reps):
-                self._run_copies(FORWARD, slab, lvl, lvl, lvl, "I%d" % (i & 1), **kw)
+                self._run_copies(FORWARD, slab, lvl, lvl, lvl, "I%d" % (i & 1), coef=coef, **kw)
             evs[1].record()
             torch.cuda.synchronize()
             out[tag + "_ms"] = evs[0].elapsed_time(evs[1]) / reps

@@ -53,6 +53,18 @@ def _worker(rank, world, port, shape, levels, out_dir):
         torch.cuda.synchronize()
         np.save(os.path.join(out_dir, f"cf{rank}.npy"), cf.cpu().numpy())
         np.save(os.path.join(out_dir, f"cr{rank}.npy"), cr.cpu().numpy())
+        # coefficients left in the j-slab layout: one re-cut per direction, the reverse rebuilds axis i first.
+        # Results live in internal buffers until the next call, which may take them as its input (chained).
+        for it in range(2):
+            tf = ct.forward_t(slab, P, *levels)
+            tf_dense = ct.t_to_dense(tf).cpu().numpy()
+            tr = ct.reverse_t(tf, P, *levels)
+            tr_host = tr.cpu().numpy()
+            tf2 = ct.forward_t(tr, P, *levels)
+            tf2_dense = ct.t_to_dense(tf2).cpu().numpy()
+        np.save(os.path.join(out_dir, f"tf{rank}.npy"), tf_dense)
+        np.save(os.path.join(out_dir, f"tr{rank}.npy"), tr_host)
+        np.save(os.path.join(out_dir, f"tg{rank}.npy"), tf2_dense)
     finally:
         dist.destroy_process_group()
 
@@ -77,3 +89,11 @@ def test_slab_volume_transform_on_gpus(tmp_path):
     assert np.array_equal(peer_r, got_r)
     for tag, want in (("cf", got_f), ("cr", got_r)):  # peer-mapped slabs filled by strided device copies
         assert np.array_equal(np.concatenate([np.load(tmp_path / f"{tag}{r}.npy") for r in range(world)]), want)
+    # transposed coefficient layout: rank g holds coef[:, g q:(g+1) q, :]
+    t_f = np.concatenate([np.load(tmp_path / f"tf{r}.npy") for r in range(world)], axis=1)
+    t_r = np.concatenate([np.load(tmp_path / f"tr{r}.npy") for r in range(world)])
+    t_g = np.concatenate([np.load(tmp_path / f"tg{r}.npy") for r in range(world)], axis=1)
+    assert np.array_equal(t_f, got_f)                                      # same passes, one re-cut fewer
+    assert np.abs(t_r - ref_r).max() <= 1e-12 * np.abs(ref_f).max()        # i-first order: rounding-level difference
+    assert np.abs(t_r - co.parallel_3d(co.FWT, co.REVERSE, "Coiflet5", got_f, *levels)).max() <= 1e-12 * np.abs(ref_f).max()
+    assert np.abs(t_g - co.transform_3d(co.FWT, co.FORWARD, "Coiflet5", t_r, *levels)).max() <= 1e-12 * np.abs(t_r).max()
