@@ -56,18 +56,21 @@ enum { JWC_FWT = 0, JWC_WPT = 1 };
 
 int jwc_version(void);
 
-/* One context = one GPU + one stream.  `device` is a CUDA ordinal.  A context serialises the
- * calls made on it; use one context per host thread (the reference's transforms are stateless,
- * BasicTransform.java:42). */
+/* One context = one GPU, one set of scratch buffers and one current stream.  `device` is a CUDA ordinal.
+ * Every entry point that takes a context holds the context's lock for its duration, so concurrent callers are
+ * serialised (the reference's transforms are stateless and thread-safe, BasicTransform.java:42; host threads
+ * that want to overlap use one context each).  The device-resident entry points only ENQUEUE work: the rule for
+ * them is one stream at a time per context - jwc_set_stream makes the new stream wait (on the device) for the
+ * work enqueued under the previous one, because both use the context's scratch buffers. */
 int jwc_create(jwc_ctx** out, int device);
 int jwc_destroy(jwc_ctx* ctx);
 /* Text of the last failure on this context (never NULL). With ctx == NULL: creation failures. */
 const char* jwc_last_error(const jwc_ctx* ctx);
 
-/* Launch on a caller-owned cudaStream_t (e.g. torch's current stream) instead of the context's
- * own.  The handle is used as given: NULL is CUDA's legacy default stream.  jwc_reset_stream goes
- * back to the context's own stream.  The host-buffer entry points always use the context's own
- * streams and are synchronous on return. */
+/* Launch on a caller-owned cudaStream_t (e.g. torch's current stream) instead of the context's own.  The handle
+ * is used as given: NULL is CUDA's legacy default stream.  jwc_reset_stream goes back to the context's own
+ * stream.  The host-buffer entry points (jwc_fwt1d ... jwc_decompose1d, jwc_compress_magnitude) always run on the
+ * context's own streams, after waiting for the caller's stream, and are synchronous on return. */
 int jwc_set_stream(jwc_ctx* ctx, void* cuda_stream);
 int jwc_reset_stream(jwc_ctx* ctx);
 int jwc_sync(jwc_ctx* ctx);

@@ -23,6 +23,13 @@ static std::mutex g_create_mu;
     }                                                                                    \
   } while (0)
 
+#define JWC_LOCK(ctx) std::lock_guard<std::recursive_mutex> lk__((ctx)->mu)
+
+// the scratch buffers are busy until everything enqueued so far on the current stream has run
+static void mark_scratch(jwc_ctx* ctx) {
+  if (ctx->scratch_ev && cudaEventRecord(ctx->scratch_ev, ctx->stream) == cudaSuccess) ctx->scratch_ev_valid = true;
+}
+
 static int fail(jwc_ctx* ctx, int status, const char* msg) {
   if (ctx) ctx->err = msg;
   return status;
@@ -76,6 +83,7 @@ extern "C" int jwc_create(jwc_ctx** out, int device) {
     cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming);
   }
   ctx->stream = ctx->own_stream;
+  cudaEventCreateWithFlags(&ctx->scratch_ev, cudaEventDisableTiming);
   const char* fg = getenv("JWC_FORCE_GENERIC");
   ctx->force_generic = fg && fg[0] == '1';
   if (const char* tune = getenv("JWC_TUNE")) {
@@ -141,6 +149,7 @@ static void free_scratch(Scratch& s) {
 
 extern "C" int jwc_destroy(jwc_ctx* ctx) {
   if (!ctx) return JWC_ERR_ARG;
+  { JWC_LOCK(ctx); }  // wait for a call still in flight on another thread; the caller must not start new ones
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   prof_clear(ctx);
@@ -152,6 +161,7 @@ extern "C" int jwc_destroy(jwc_ctx* ctx) {
     if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
     if (ctx->ev_out[i]) cudaEventDestroy(ctx->ev_out[i]);
   }
+  if (ctx->scratch_ev) cudaEventDestroy(ctx->scratch_ev);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
   if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
@@ -167,20 +177,32 @@ extern "C" const char* jwc_last_error(const jwc_ctx* ctx) {
   return copy.c_str();
 }
 
+// Switching streams: work already enqueued under the old stream may still be using the scratch buffers, so the
+// new stream first waits (on the device, no host sync) for the event recorded after the last such launch.
+static int switch_stream(jwc_ctx* ctx, cudaStream_t next) {
+  if (next != ctx->stream && ctx->scratch_ev_valid) {
+    JWC_CUDA(ctx, cudaSetDevice(ctx->device));
+    JWC_CUDA(ctx, cudaStreamWaitEvent(next, ctx->scratch_ev, 0));
+  }
+  ctx->stream = next;
+  return JWC_OK;
+}
+
 extern "C" int jwc_set_stream(jwc_ctx* ctx, void* cuda_stream) {
   if (!ctx) return JWC_ERR_ARG;
-  ctx->stream = static_cast<cudaStream_t>(cuda_stream);
-  return JWC_OK;
+  JWC_LOCK(ctx);
+  return switch_stream(ctx, static_cast<cudaStream_t>(cuda_stream));
 }
 
 extern "C" int jwc_reset_stream(jwc_ctx* ctx) {
   if (!ctx) return JWC_ERR_ARG;
-  ctx->stream = ctx->own_stream;
-  return JWC_OK;
+  JWC_LOCK(ctx);
+  return switch_stream(ctx, ctx->own_stream);
 }
 
 extern "C" int jwc_sync(jwc_ctx* ctx) {
   if (!ctx) return JWC_ERR_ARG;
+  JWC_LOCK(ctx);
   JWC_CUDA(ctx, cudaSetDevice(ctx->device));
   JWC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return JWC_OK;
@@ -198,6 +220,7 @@ static void prof_clear(jwc_ctx* ctx) {
 
 extern "C" int jwc_profile_enable(jwc_ctx* ctx, int on) {
   if (!ctx) return JWC_ERR_ARG;
+  JWC_LOCK(ctx);
   JWC_CUDA(ctx, cudaSetDevice(ctx->device));
   prof_clear(ctx);
   ctx->prof_on = on != 0;
@@ -208,6 +231,7 @@ extern "C" int jwc_profile_enable(jwc_ctx* ctx, int on) {
 // recorded launches, then clears the records.
 extern "C" int jwc_profile_report(jwc_ctx* ctx, char* buf, size_t size) {
   if (!ctx || !buf || size == 0) return JWC_ERR_ARG;
+  JWC_LOCK(ctx);
   JWC_CUDA(ctx, cudaSetDevice(ctx->device));
   struct Acc { const char* name; int n; double ms, units; int levels; };
   std::vector<Acc> acc;
@@ -240,6 +264,7 @@ extern "C" int jwc_profile_report(jwc_ctx* ctx, char* buf, size_t size) {
 extern "C" int jwc_set_wavelet(jwc_ctx* ctx, int L, const double* sDe, const double* wDe,
                                const double* sRe, const double* wRe, int* wid) {
   if (!ctx) return JWC_ERR_ARG;
+  JWC_LOCK(ctx);
   if (!sDe || !wDe || !sRe || !wRe || !wid) return fail(ctx, JWC_ERR_ARG, "jwc_set_wavelet: null argument");
   if (L < 2 || L > JWC_MAX_TAPS || (L & 1))
     return fail(ctx, JWC_ERR_ARG, "jwc_set_wavelet: filter length must be even and within 2..40");
@@ -281,6 +306,7 @@ static int check_axis(jwc_ctx* ctx, int n, int level) {
 
 static int check_common(jwc_ctx* ctx, int wid, int kind, int dir, const void* in, const void* out) {
   if (!ctx) return JWC_ERR_ARG;
+  JWC_LOCK(ctx);
   if (wid < 0 || wid >= int(ctx->wavelets.size())) return fail(ctx, JWC_ERR_ARG, "unknown wavelet handle");
   if (kind != JWC_FWT && kind != JWC_WPT) return fail(ctx, JWC_ERR_ARG, "kind must be JWC_FWT or JWC_WPT");
   if (dir != JWC_FORWARD && dir != JWC_REVERSE) return fail(ctx, JWC_ERR_ARG, "dir must be JWC_FORWARD or JWC_REVERSE");
@@ -303,6 +329,7 @@ static int axis_dev(jwc_ctx* ctx, int wid, int kind, int dir, const double* in, 
   if (overlaps(in, out, outer * n * inner)) return fail(ctx, JWC_ERR_ARG, "in and out overlap");
   JWC_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaError_t e = run_axis(ctx, ctx->wavelets[wid], kind, dir, in, out, outer, n, inner, level);
+  mark_scratch(ctx);
   if (e != cudaSuccess) {
     ctx->err = std::string("axis transform: ") + cudaGetErrorString(e);
     return JWC_ERR_CUDA;
@@ -314,12 +341,14 @@ extern "C" int jwc_axis_dev(jwc_ctx* ctx, int wid, int kind, int dir, const doub
                             int64_t outer, int n, int64_t inner, int level) {
   int st = check_common(ctx, wid, kind, dir, in, out);
   if (st) return st;
+  JWC_LOCK(ctx);
   return axis_dev(ctx, wid, kind, dir, in, out, outer, n, inner, level);
 }
 
 extern "C" int jwc_axis_dev_remote(jwc_ctx* ctx, int wid, int kind, int dir, const double* in, int64_t outer, int n,
                                    int64_t inner, int level, const jwc_remote_map* map) {
   if (!ctx) return JWC_ERR_ARG;
+  JWC_LOCK(ctx);
   if (!map) return fail(ctx, JWC_ERR_ARG, "null remote map");
   int st = check_common(ctx, wid, kind, dir, in, map->peer[0]);
   if (st) return st;
@@ -345,6 +374,7 @@ extern "C" int jwc_axis_dev_remote(jwc_ctx* ctx, int wid, int kind, int dir, con
   ctx->remote = &rm;
   cudaError_t e = run_axis(ctx, ctx->wavelets[wid], kind, dir, in, rm.peer[0], outer, n, inner, level);
   ctx->remote = nullptr;
+  mark_scratch(ctx);
   if (e == cudaErrorNotSupported) return fail(ctx, JWC_ERR_ARG, "remote stores: shape not covered by the fused kernels");
   if (e != cudaSuccess) {
     ctx->err = std::string("axis transform: ") + cudaGetErrorString(e);
@@ -357,6 +387,7 @@ static int t1d_dev(jwc_ctx* ctx, int wid, int kind, int dir, const double* in, d
                    int64_t batch, int n, int level) {
   int st = check_common(ctx, wid, kind, dir, in, out);
   if (st) return st;
+  JWC_LOCK(ctx);
   return axis_dev(ctx, wid, kind, dir, in, out, batch, n, 1, level);
 }
 
@@ -388,6 +419,7 @@ static int t2d_dev(jwc_ctx* ctx, int wid, int kind, int dir, const double* in, d
                    int64_t batch, int rows, int cols, int lvlM, int lvlN) {
   int st = check_common(ctx, wid, kind, dir, in, out);
   if (st) return st;
+  JWC_LOCK(ctx);
   // the reference transforms rows first (forward) / columns first (reverse): report in that order
   if (dir == JWC_FORWARD) {
     if ((st = check_axis(ctx, cols, lvlN)) || (st = check_axis(ctx, rows, lvlM))) return st;
@@ -425,6 +457,7 @@ static int t3d_dev(jwc_ctx* ctx, int wid, int kind, int dir, const double* in, d
                    int Q, int R, int lvlP, int lvlQ, int lvlR) {
   int st = check_common(ctx, wid, kind, dir, in, out);
   if (st) return st;
+  JWC_LOCK(ctx);
   if (dir == JWC_FORWARD) {
     if ((st = check_axis(ctx, R, lvlQ)) || (st = check_axis(ctx, Q, lvlP))) return st;
   } else {
@@ -489,6 +522,7 @@ extern "C" int jwc_aed1d_dev(jwc_ctx* ctx, int wid, int kind, int dir, const dou
                              int64_t batch, int n) {
   int st = check_common(ctx, wid, kind, dir, in, out);
   if (st) return st;
+  JWC_LOCK(ctx);
   return aed_dev(ctx, wid, kind, dir, in, out, batch, n);
 }
 
@@ -544,6 +578,7 @@ extern "C" int jwc_decompose1d_dev(jwc_ctx* ctx, int wid, int kind, const double
                                    int n) {
   int st = check_common(ctx, wid, kind, JWC_FORWARD, in, out);
   if (st) return st;
+  JWC_LOCK(ctx);
   return decompose_dev(ctx, wid, kind, in, out, batch, n);
 }
 
@@ -551,6 +586,7 @@ extern "C" int jwc_decompose1d_dev(jwc_ctx* ctx, int wid, int kind, const double
 static int compress_dev(jwc_ctx* ctx, const double* in, double* out, int64_t count, double threshold,
                         double* magnitude_dev) {
   if (!ctx) return JWC_ERR_ARG;
+  JWC_LOCK(ctx);
   if (!in || !out) return fail(ctx, JWC_ERR_ARG, "null data pointer");
   if (!(threshold > 0.)) return fail(ctx, JWC_ERR_ARG, "Compressor - given threshold should be larger than zero!");
   if (count < 1) return fail(ctx, JWC_ERR_ARG, "Compressor - empty array");
@@ -560,6 +596,7 @@ static int compress_dev(jwc_ctx* ctx, const double* in, double* out, int64_t cou
   if (st) return st;
   double* scratch = static_cast<double*>(ctx->scratch[3].ptr);
   cudaError_t e = launch_compress_magnitude(ctx, in, out, count, threshold, scratch, blocks);
+  mark_scratch(ctx);
   if (e != cudaSuccess) {
     ctx->err = std::string("compress: ") + cudaGetErrorString(e);
     return JWC_ERR_CUDA;
@@ -578,6 +615,7 @@ extern "C" int jwc_compress_magnitude_dev(jwc_ctx* ctx, const double* in, double
 extern "C" int jwc_compress_magnitude(jwc_ctx* ctx, const double* in, double* out, int64_t count, double threshold,
                                       double* magnitude) {
   if (!ctx) return JWC_ERR_ARG;
+  JWC_LOCK(ctx);
   if (!in || !out) return fail(ctx, JWC_ERR_ARG, "null data pointer");
   if (!(threshold > 0.)) return fail(ctx, JWC_ERR_ARG, "Compressor - given threshold should be larger than zero!");
   if (count < 1) return fail(ctx, JWC_ERR_ARG, "Compressor - empty array");
@@ -675,6 +713,7 @@ static int t1d_host(jwc_ctx* ctx, int wid, int kind, int dir, const double* in, 
                     int64_t batch, int n, int level) {
   int st = check_common(ctx, wid, kind, dir, in, out);
   if (st) return st;
+  JWC_LOCK(ctx);
   if ((st = check_axis(ctx, n, level))) return st;
   if (batch < 0) return fail(ctx, JWC_ERR_ARG, "negative batch");
   return staged(ctx, in, out, batch, n, [&](const double* di, double* dout, int64_t cnt) {
@@ -695,6 +734,7 @@ extern "C" int jwc_aed1d(jwc_ctx* ctx, int wid, int kind, int dir, const double*
                          int n) {
   int st = check_common(ctx, wid, kind, dir, in, out);
   if (st) return st;
+  JWC_LOCK(ctx);
   if (n < 1) return fail(ctx, JWC_ERR_ARG, "the supported number for decomposition is smaller than one");
   if (batch < 0) return fail(ctx, JWC_ERR_ARG, "negative batch");
   return staged(ctx, in, out, batch, n, [&](const double* di, double* dout, int64_t cnt) {
@@ -707,10 +747,17 @@ extern "C" int jwc_aed1d(jwc_ctx* ctx, int wid, int kind, int dir, const double*
 extern "C" int jwc_decompose1d(jwc_ctx* ctx, int wid, int kind, const double* in, double* out, int64_t batch, int n) {
   int st = check_common(ctx, wid, kind, JWC_FORWARD, in, out);
   if (st) return st;
+  JWC_LOCK(ctx);
   if ((st = check_axis(ctx, n, 0))) return st;
   if (batch < 0) return fail(ctx, JWC_ERR_ARG, "negative batch");
   if (batch == 0) return JWC_OK;
   JWC_CUDA(ctx, cudaSetDevice(ctx->device));
+  // host-buffer entry points run on the context's own stream (include/jwave_cuda.h), whatever jwc_set_stream chose
+  struct OwnStream {
+    jwc_ctx* c; cudaStream_t user;
+    explicit OwnStream(jwc_ctx* c_) : c(c_), user(c_->stream) { switch_stream(c, c->own_stream); }
+    ~OwnStream() { cudaStreamSynchronize(c->own_stream); switch_stream(c, user); }
+  } own(ctx);
   const int64_t sig = int64_t(exponent(n) + 1) * n;
   int64_t per_chunk = int64_t(ctx->staging_bytes / (size_t(sig) * sizeof(double)));
   if (per_chunk < 1) per_chunk = 1;
@@ -733,6 +780,7 @@ static int t2d_host(jwc_ctx* ctx, int wid, int kind, int dir, const double* in, 
                     int64_t batch, int rows, int cols, int lvlM, int lvlN) {
   int st = check_common(ctx, wid, kind, dir, in, out);
   if (st) return st;
+  JWC_LOCK(ctx);
   if (dir == JWC_FORWARD) {
     if ((st = check_axis(ctx, cols, lvlN)) || (st = check_axis(ctx, rows, lvlM))) return st;
   } else {
@@ -757,6 +805,7 @@ static int t3d_host(jwc_ctx* ctx, int wid, int kind, int dir, const double* in, 
                     int Q, int R, int lvlP, int lvlQ, int lvlR) {
   int st = check_common(ctx, wid, kind, dir, in, out);
   if (st) return st;
+  JWC_LOCK(ctx);
   if (P <= 0 || Q <= 0 || R <= 0) return fail(ctx, JWC_ERR_NOT_BINARY, "given array length is not 2^p | p E N");
   const size_t keep = ctx->staging_bytes;
   ctx->staging_bytes = size_t(-1) / 2;  // one volume is one item
@@ -780,42 +829,49 @@ extern "C" int jwc_wpt3d(jwc_ctx* ctx, int wid, int dir, const double* in, doubl
 
 extern "C" int jwc_dev_alloc(jwc_ctx* ctx, size_t bytes, void** dptr) {
   if (!ctx || !dptr) return JWC_ERR_ARG;
+  JWC_LOCK(ctx);
   JWC_CUDA(ctx, cudaSetDevice(ctx->device));
   JWC_CUDA(ctx, cudaMalloc(dptr, bytes ? bytes : 1));
   return JWC_OK;
 }
 extern "C" int jwc_dev_free(jwc_ctx* ctx, void* dptr) {
   if (!ctx) return JWC_ERR_ARG;
+  JWC_LOCK(ctx);
   JWC_CUDA(ctx, cudaSetDevice(ctx->device));
   JWC_CUDA(ctx, cudaFree(dptr));
   return JWC_OK;
 }
 extern "C" int jwc_h2d(jwc_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
   if (!ctx || !dst_dev || !src_host) return JWC_ERR_ARG;
+  JWC_LOCK(ctx);
   JWC_CUDA(ctx, cudaSetDevice(ctx->device));
   JWC_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
   return JWC_OK;
 }
 extern "C" int jwc_d2h(jwc_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
   if (!ctx || !dst_host || !src_dev) return JWC_ERR_ARG;
+  JWC_LOCK(ctx);
   JWC_CUDA(ctx, cudaSetDevice(ctx->device));
   JWC_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   return JWC_OK;
 }
 extern "C" int jwc_host_alloc_pinned(jwc_ctx* ctx, size_t bytes, void** hptr) {
   if (!ctx || !hptr) return JWC_ERR_ARG;
+  JWC_LOCK(ctx);
   JWC_CUDA(ctx, cudaSetDevice(ctx->device));
   JWC_CUDA(ctx, cudaHostAlloc(hptr, bytes ? bytes : 1, cudaHostAllocDefault));
   return JWC_OK;
 }
 extern "C" int jwc_host_free_pinned(jwc_ctx* ctx, void* hptr) {
   if (!ctx) return JWC_ERR_ARG;
+  JWC_LOCK(ctx);
   JWC_CUDA(ctx, cudaFreeHost(hptr));
   return JWC_OK;
 }
 extern "C" int jwc_copy2d_dev(jwc_ctx* ctx, void* dst, size_t dpitch, const void* src, size_t spitch, size_t width,
                               size_t height, void* cuda_stream) {
   if (!ctx || !dst || !src) return JWC_ERR_ARG;
+  JWC_LOCK(ctx);
   if (width == 0 || height == 0) return JWC_OK;
   if (dpitch < width || spitch < width) return fail(ctx, JWC_ERR_ARG, "jwc_copy2d_dev: pitch smaller than the row");
   JWC_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -826,6 +882,7 @@ extern "C" int jwc_copy2d_dev(jwc_ctx* ctx, void* dst, size_t dpitch, const void
 
 extern "C" int jwc_set_staging_bytes(jwc_ctx* ctx, size_t bytes) {
   if (!ctx || bytes < sizeof(double)) return JWC_ERR_ARG;
+  JWC_LOCK(ctx);
   ctx->staging_bytes = bytes;
   return JWC_OK;
 }

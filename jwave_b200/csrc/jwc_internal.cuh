@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -98,6 +99,13 @@ struct Scratch {
 }  // namespace jwc
 
 struct jwc_ctx {
+  // Every entry point that takes a context holds this lock for its duration: a context is one GPU, one set of
+  // scratch buffers and one "current stream", so concurrent callers are serialised here (include/jwave_cuda.h).
+  std::recursive_mutex mu;
+  // Recorded on ctx->stream after the last launch that touches the scratch buffers; jwc_set_stream makes the
+  // new stream wait for it, so work enqueued under different streams never overlaps on the same scratch.
+  cudaEvent_t scratch_ev = nullptr;
+  bool scratch_ev_valid = false;
   int device = 0;
   int sm_count = 148;
   size_t smem_optin = 0;

@@ -2,7 +2,12 @@
 
 torch is plumbing here (device memory, streams, torch.distributed); the arithmetic is
 libjwave_cuda.so's *_dev functions, enqueued on torch's current stream so torch.cuda.Event
-brackets them."""
+brackets them.
+
+One stream at a time per context: every call tells the library which torch stream is current
+(jwc_set_stream); when that changes, the library makes the new stream wait on the device for the work
+enqueued under the old one, because both use the context's scratch buffers (include/jwave_cuda.h).  Callers
+that want two streams to overlap use two DeviceTransforms (two contexts)."""
 import torch
 
 from . import _lib

@@ -58,19 +58,21 @@ class CudaContext:
 
     def register(self, wavelet):
         """jwc_set_wavelet with the four getter arrays (Wavelet.java:178-219)."""
-        key = id(wavelet)
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (
+            wavelet.getScalingDeComposition(), wavelet.getWaveletDeComposition(),
+            wavelet.getScalingReConstruction(), wavelet.getWaveletReConstruction())]
+        # keyed by the tap CONTENTS: builders hand out a fresh Wavelet object per call, and the C side keeps
+        # every registered filter set until the context is destroyed
+        key = (wavelet.getMotherWavelength(),) + tuple(a.tobytes() for a in arrs)
         with self.lock:
             if key in self._wids:
-                return self._wids[key][0]
-            arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (
-                wavelet.getScalingDeComposition(), wavelet.getWaveletDeComposition(),
-                wavelet.getScalingReConstruction(), wavelet.getWaveletReConstruction())]
+                return self._wids[key]
             wid = C.c_int(-1)
             dp = C.POINTER(C.c_double)
             st = self._lib.jwc_set_wavelet(self.handle, wavelet.getMotherWavelength(),
                                            *[a.ctypes.data_as(dp) for a in arrs], C.byref(wid))
             self.check(st, "jwc_set_wavelet")
-            self._wids[key] = (wid.value, wavelet)  # keep the wavelet alive: id() is the key
+            self._wids[key] = wid.value
             return wid.value
 
     def last_error(self):
@@ -371,6 +373,8 @@ class _CudaWaveletTransform(WaveletTransform):
 
     def forwardBatch2D(self, mats, lvlM=None, lvlN=None):
         mats = _as_f64(mats)
+        if mats.ndim != 3:
+            raise JWaveFailure("forwardBatch2D - expected a [batch][rows][cols] array")
         b, rows, cols = mats.shape
         lvlN = self._check(cols, lvlN, "forwardBatch2D")
         lvlM = self._check(rows, lvlM, "forwardBatch2D")
@@ -378,6 +382,8 @@ class _CudaWaveletTransform(WaveletTransform):
 
     def reverseBatch2D(self, mats, lvlM=None, lvlN=None):
         mats = _as_f64(mats)
+        if mats.ndim != 3:
+            raise JWaveFailure("reverseBatch2D - expected a [batch][rows][cols] array")
         b, rows, cols = mats.shape
         lvlM = self._check(rows, lvlM, "reverseBatch2D")
         lvlN = self._check(cols, lvlN, "reverseBatch2D")

@@ -213,11 +213,11 @@ def test_parallel_transform_ports_match_the_sequential_drivers():
             assert np.array_equal(co.parallel_2d(co.FWT, direction, "Daubechies4", imgs, 5, 6, threads), want)
     vol = rng.standard_normal((16, 8, 32))
     for kind in (co.FWT, co.WPT):
-        f = co.transform_3d(kind, co.FORWARD, "Coiflet1", vol, 3, 4, 5)   # (lvlP, lvlQ, lvlR) with the F5 shift
+        f = co.transform_3d(kind, co.FORWARD, "Coiflet1", vol, 3, 5, 4)   # (lvlP, lvlQ, lvlR) with the F5 shift: Q = 8 gets 3, R = 32 gets 5, P = 16 gets 4
         for threads in (1, 3):
-            assert np.array_equal(co.parallel_3d(kind, co.FORWARD, "Coiflet1", vol, 3, 4, 5, threads), f)
-        r = co.transform_3d(kind, co.REVERSE, "Coiflet1", f, 3, 4, 5)
-        pr = co.parallel_3d(kind, co.REVERSE, "Coiflet1", f, 3, 4, 5, 4)
+            assert np.array_equal(co.parallel_3d(kind, co.FORWARD, "Coiflet1", vol, 3, 5, 4, threads), f)
+        r = co.transform_3d(kind, co.REVERSE, "Coiflet1", f, 3, 5, 4)
+        pr = co.parallel_3d(kind, co.REVERSE, "Coiflet1", f, 3, 5, 4, 4)
         assert np.abs(pr - r).max() <= 1e-12 * np.abs(f).max()
         assert np.abs(pr - vol).max() <= 1e-9
     with pytest.raises(co.OracleError):
