@@ -240,13 +240,11 @@ class PeerSlabVolumeTransform:
             src = self._y.data_ptr() + ((c * P + d * p) * qc * R) * 8
             self.dev.copy2d(dst, Q * R * 8, src, row, row, p, stream=cs[(c * W + k) % len(cs)])
 
-    def _run_copies(self, direction, slab, lvlP, lvlQ, lvlR, key, compute=True, copies=True, coef="i"):
-        """direction FORWARD: i-slab in -> coefficients in the i-slab layout (coef="i", two re-cuts) or left in the
-        j-slab layout (coef="j", ONE re-cut).  REVERSE: coefficients in that layout -> i-slab of samples; with
-        coef="j" the i axis is rebuilt first - the order of ParallelTransform.reverse (ParallelTransform.java:193),
-        which differs from BasicTransform's by rounding only (the axis passes act on different indices).
-        Each re-cut is cut into C chunks whose copies run on the copy engines (copy stream) beside the next
-        chunk's axis passes; only the last chunk of a re-cut is exposed.  `compute` / `copies`: measure()."""
+    def _run_copies(self, direction, slab, lvlP, lvlQ, lvlR, key, compute=True, copies=True):
+        """The reference's layout on both sides (i-slabs in, i-slabs out): two re-cuts per direction, each cut into
+        C chunks whose copies run on the copy engines (copy streams) beside the next chunk's axis passes; only the
+        last chunk of a re-cut is exposed.  The j-slab is held as C dense sub-slabs [C][P][q/C][R] so that the
+        second re-cut can follow the i pass sub-slab by sub-slab.  `compute` / `copies`: measure()."""
         p, q, P, Q, R, C = self.p, self.q, self.P, self.Q, self.R, self.chunks
         dev = self.dev
         comp, cs = torch.cuda.current_stream(dev.device), self._copy_streams
@@ -258,54 +256,124 @@ class PeerSlabVolumeTransform:
                 comp.wait_stream(st)
         # No barrier on entry: every rank passed the closing barrier of the previous call only after its own i
         # passes had read its j-slab, and after the local passes of that call had read the i-slab it was given.
-        if direction == FORWARD or coef == "i":
-            for c in range(C):                           # re-cut 1: i-slabs -> j-slabs, behind the k / j passes
-                if compute:
-                    self._local_ij(direction, slab, slice(c * S, (c + 1) * S), lvlP, lvlQ)
-                if copies:
-                    self._send_to_j(c, comp, cs)
-            join_copies()
-            self._hdl["J"].barrier()                     # every rank's rows have landed in my j-slab
-            src_j = Jc
-        else:
-            src_j = slab                                 # coefficients already in the j-slab layout [C][P][qc][R]
-        last_recut = not (direction == FORWARD and coef == "j")
-        self._y = (self._tmp if (direction == FORWARD or coef == "i") else self._tmp2).view(C, P, qc, R)
+        for c in range(C):                               # re-cut 1: i-slabs -> j-slabs, behind the k / j passes
+            if compute:
+                self._local_ij(direction, slab, slice(c * S, (c + 1) * S), lvlP, lvlQ)
+            if copies:
+                self._send_to_j(c, comp, cs)
+        join_copies()
+        self._hdl["J"].barrier()                         # every rank's rows have landed in my j-slab
+        self._y = self._tmp.view(C, P, qc, R)
         for c in range(C):                               # the i pass, sub-slab by sub-slab
             if compute:
-                dev.axis(FWT, direction, src_j[c], 1, P, qc * R, lvlR, out=self._y[c])
-            if copies and last_recut:                    # re-cut 2: j-slabs -> i-slabs
+                dev.axis(FWT, direction, Jc[c], 1, P, qc * R, lvlR, out=self._y[c])
+            if copies:                                   # re-cut 2: j-slabs -> i-slabs
                 self._send_to_i(c, key, comp, cs)
-        if not last_recut:
-            self._hdl["J"].barrier()                     # closing barrier: my j-slab may be refilled by the next call
-            return self._y                               # forward, coef="j": [C][P][qc][R], no second re-cut
         join_copies()
         self._hdl[key].barrier()
-        out = self._bufs[key].view(p, Q, R)
-        if direction == REVERSE and coef == "j":         # the slices are rebuilt last, locally
+        return self._bufs[key].view(p, Q, R)
+
+    # ---- coefficients left in the j-slab layout: ONE re-cut per direction ---------------------------------
+    # Plain layouts on both sides (i-slab [p][Q][R], j-slab [P][q][R]), so every 2-D copy of a re-cut moves rows of
+    # q * R contiguous doubles (1 MiB for 1024^3 on 8 GPUs): the copy engines' rate over NVLink falls with the row
+    # width (715 GB/s at 1 MiB rows, 380 GB/s at 256 KiB - profiles/r02_slab_recut.md), which is what the
+    # sub-slab form above pays for being able to overlap its second re-cut.
+    def _copy_rows_to_j(self, c, cs):
+        """slices chunk c of my k/j-pass result (self._tmp2, i-slab) -> rows [rank p + c S, + S) of every j-slab"""
+        p, q, Q, R, rank, W = self.p, self.q, self.Q, self.R, self.rank, self.world
+        S = p // self.chunks
+        for k in range(W):  # my own block first, then round the ring so the peers are hit evenly
+            d = (rank + k) % W
+            dst = self._ptrs["J"][d] + ((rank * p + c * S) * q * R) * 8
+            src = self._tmp2.data_ptr() + ((c * S) * Q * R + d * q * R) * 8
+            self.dev.copy2d(dst, q * R * 8, src, Q * R * 8, q * R * 8, S, stream=cs[k % len(cs)])
+
+    def _copy_rows_to_i(self, c, key, cs):
+        """rows of slices chunk c of every rank's i range, from my i-pass result (self._tmp2, j-slab) -> their i-slabs"""
+        p, q, Q, R, rank, W = self.p, self.q, self.Q, self.R, self.rank, self.world
+        S = p // self.chunks
+        for k in range(W):
+            d = (rank + k) % W
+            dst = self._ptrs[key][d] + ((c * S) * Q * R + rank * q * R) * 8
+            src = self._tmp2.data_ptr() + ((d * p + c * S) * q * R) * 8
+            self.dev.copy2d(dst, Q * R * 8, src, q * R * 8, q * R * 8, S, stream=cs[k % len(cs)])
+
+    def _forward_t(self, slab, lvlP, lvlQ, lvlR, compute=True, copies=True):
+        p, q, P, Q, R, C = self.p, self.q, self.P, self.Q, self.R, self.chunks
+        comp, cs = torch.cuda.current_stream(self.dev.device), self._copy_streams
+        S = p // C
+        for c in range(C):                               # k and j passes of chunk c; its rows leave behind them
             if compute:
-                self._local_ij(REVERSE, out, slice(0, p), lvlP, lvlQ)
-            return self._tmp2.view(p, Q, R)
+                self._local_ij(FORWARD, slab, slice(c * S, (c + 1) * S), lvlP, lvlQ)
+            if copies:
+                ev = torch.cuda.Event()
+                ev.record(comp)
+                for st in cs:
+                    st.wait_event(ev)
+                self._copy_rows_to_j(c, cs)
+        for st in cs:
+            comp.wait_stream(st)
+        self._hdl["J"].barrier()                         # every rank's rows have landed in my j-slab
+        y = self._tmp.view(P, q, R)
+        if compute:
+            self.dev.axis(FWT, FORWARD, self._bufs["J"].view(P, q, R), 1, P, q * R, lvlR, out=y)
+        self._hdl["J"].barrier()                         # closing barrier: my j-slab may be refilled by the next call
+        return y
+
+    def _reverse_t(self, coef, lvlP, lvlQ, lvlR, key, compute=True, copies=True):
+        p, q, P, Q, R, C = self.p, self.q, self.P, self.Q, self.R, self.chunks
+        comp, cs = torch.cuda.current_stream(self.dev.device), self._copy_streams
+        S = p // C
+        other = "I1" if key == "I0" else "I0"
+        I, out = self._bufs[key].view(p, Q, R), self._bufs[other].view(p, Q, R)
+        a = self._tmp.view(p, Q, R)
+        if compute:                                      # axis i first (ParallelTransform.java:193)
+            self.dev.axis(FWT, REVERSE, coef, 1, P, q * R, lvlR, out=self._tmp2.view(P, q, R))
+        ev = torch.cuda.Event()
+        ev.record(comp)
+        landed = []
+        for st in cs:
+            st.wait_event(ev)
+        for c in range(C):                               # the re-cut runs AHEAD of the slices' passes, chunk by chunk
+            if copies:
+                self._copy_rows_to_i(c, key, cs)
+            evs = []
+            for st in cs:
+                e = torch.cuda.Event()
+                e.record(st)
+                evs.append(e)
+            landed.append(evs)
+        for c in range(C):
+            for e in landed[c]:
+                comp.wait_event(e)
+            self._hdl[key].barrier()                     # chunk c of every rank has landed in my i-slab
+            if compute:                                  # BasicTransform.java:602-659 per slice: columns, then rows
+                sl = slice(c * S, (c + 1) * S)
+                self.dev.axis(FWT, REVERSE, I[sl], S, Q, R, lvlP, out=a[sl])
+                self.dev.axis(FWT, REVERSE, a[sl], S * Q, R, 1, lvlQ, out=out[sl])
         return out
 
     def forward_t(self, slab, P, lvlP, lvlQ, lvlR):
-        """Forward transform that leaves the coefficients in the j-slab layout [C][P][q/C][R] (rank g owns
-        j in [g q, (g+1) q)): one re-cut instead of two.  `coef_to_i_slab_order` gives the
-        dense [P][q][R] copy of it.  The result lives in an internal buffer: valid until the next call."""
-        self._flip ^= 1
-        return self._run_copies(FORWARD, slab, lvlP, lvlQ, lvlR, "I%d" % self._flip, coef="j")
+        """Forward transform that leaves the coefficients in the j-slab layout [P][q][R] (rank g owns
+        j in [g q, (g+1) q)): one re-cut instead of two.  The result lives in an internal
+        buffer: valid until the next call."""
+        if self.exchange != "copies" or tuple(slab.shape) != (self.p, self.Q, self.R):
+            raise ValueError("forward_t: exchange='copies' and this rank's [P/W][Q][R] slab")
+        return self._forward_t(slab, lvlP, lvlQ, lvlR)
 
     def reverse_t(self, coef_t, P, lvlP, lvlQ, lvlR):
-        """Reverse of forward_t: j-slab coefficients in, i-slab of samples out (internal buffer: valid until the
-        next call, which may take it as its input)."""
+        """Reverse of forward_t: j-slab coefficients [P][q][R] in, i-slab of samples out (an internal buffer, valid
+        until the next-but-one call; the next call may take it as its input).  Axis i is rebuilt first - the order of
+        ParallelTransform.reverse (ParallelTransform.java:193), rounding-level different from BasicTransform's."""
+        if self.exchange != "copies" or tuple(coef_t.shape) != (self.P, self.q, self.R):
+            raise ValueError("reverse_t: exchange='copies' and this rank's [P][Q/W][R] coefficients")
         self._flip ^= 1
-        return self._run_copies(REVERSE, coef_t, lvlP, lvlQ, lvlR, "I%d" % self._flip, coef="j")
+        return self._reverse_t(coef_t, lvlP, lvlQ, lvlR, "I%d" % self._flip)
 
     @staticmethod
     def t_to_dense(coef_t):
-        """[C][P][q/C][R] -> the dense j-slab [P][q][R] (a copy)."""
-        C, P, qc, R = coef_t.shape
-        return coef_t.permute(1, 0, 2, 3).reshape(P, C * qc, R)
+        """the j-slab coefficients as a dense [P][q][R] array (they already are)"""
+        return coef_t
 
     def exchange_bytes(self, slab=None):
         """Bytes this rank sends to OTHER GPUs per re-cut (the NVLink term of the step)."""
@@ -317,13 +385,18 @@ class PeerSlabVolumeTransform:
         if self.exchange != "copies":
             return {}
         out = {}
+
+        def call(i, **kw):
+            if coef == "j":
+                return self._forward_t(slab, lvl, lvl, lvl, **kw)
+            return self._run_copies(FORWARD, slab, lvl, lvl, lvl, "I%d" % (i & 1), **kw)
         for tag, kw in (("full", {}), ("compute_only", {"copies": False}), ("copies_only", {"compute": False})):
             evs = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-            self._run_copies(FORWARD, slab, lvl, lvl, lvl, "I0", coef=coef, **kw)
+            call(0, **kw)
             torch.cuda.synchronize()
             evs[0].record()
             for i in range(reps):
-                self._run_copies(FORWARD, slab, lvl, lvl, lvl, "I%d" % (i & 1), coef=coef, **kw)
+                call(i, **kw)
             evs[1].record()
             torch.cuda.synchronize()
             out[tag + "_ms"] = evs[0].elapsed_time(evs[1]) / reps
