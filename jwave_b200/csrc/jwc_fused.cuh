@@ -9,6 +9,19 @@ namespace jwc {
 constexpr int kThreads = 256;  // upper bound of the CTA size of the strided kernels (launch bound)
 constexpr int kR = 4;          // consecutive outputs (per filter) one thread produces per step
 
+// Thread index with the CTA's warps rotated by the CTA number (JWC_TUNE rot_warps=1; OFF by default).  The
+// tile kernels give their warps different roles - four main warps and a fifth, lighter tail warp.  If the
+// hardware placed warp w of every CTA on SM sub-partition w mod 4, the tail warps of all resident CTAs would
+// share sub-partition 0 with a main warp; rotating the roles with blockIdx was meant to spread them.  Measured:
+// it is 5-7 % SLOWER on both the WPT and the FWT tile kernels (profiles/r02_ab_rot_warps.txt: Symlet8 WPT forward
+// 0.725 -> 0.673 of the FP64 roofline, Daubechies4 FWT forward 0.976 -> 0.919 of the HBM peak), i.e. the
+// unrotated placement is already the balanced one.  Kept as a switch because it is the experiment that says so.
+__device__ __forceinline__ int rotated_tid(int rot) {
+  if (!rot) return threadIdx.x;
+  const unsigned nw = blockDim.x >> 5, w = threadIdx.x >> 5;
+  return int((((w + blockIdx.x) % nw) << 5) | (threadIdx.x & 31));
+}
+
 // Padded shared-memory layout of a line segment: interleaved samples as double2 (x[2k], x[2k+1]), one
 // pad slot after every 4 double2.  A thread that produces outputs 4g..4g+3 reads the window
 // k = 4g .. 4g + L/2 + 2; consecutive threads are 5 slots (80 B) apart, so the 8 lanes of a

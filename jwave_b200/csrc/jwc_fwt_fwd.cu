@@ -38,7 +38,7 @@ template <int L, bool RESIDENT, int R = 4>
 __global__ void __launch_bounds__(384)
 k_fwt_fwd(const __grid_constant__ Taps taps, const FwtFwdArgs a) {
   extern __shared__ double2 smem2[];
-  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int tid = rotated_tid(a.rot), nthr = blockDim.x;
 
   if constexpr (!RESIDENT) {
     // ---------------- tile mode ----------------
@@ -197,6 +197,7 @@ static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, FwtFwdArgs a, bool r
   }
   prof_begin(ctx, resident ? "k_fwt_fwd:resident" : "k_fwt_fwd:tile", double(a.lines) * a.h, a.m);
   a.tail = (!resident && ctx->fwd_tail && L <= kTailMaxL) ? 1 : 0;
+  a.rot = (a.tail && ctx->rot_warps) ? 1 : 0;
   kern<<<grid, resident ? ctx->res_threads : ctx->fwd_threads + 32 * a.tail, smem, ctx->stream>>>(taps, a);
   prof_end(ctx);
   ctx->launches++;

@@ -99,7 +99,7 @@ template <int L, bool RESIDENT, int kRS>
 __global__ void __launch_bounds__(384)
 k_fwt_rev(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevArgs a) {
   extern __shared__ double2 smem2[];
-  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int tid = rotated_tid(a.rot), nthr = blockDim.x;
   const int m = a.m, h0 = a.h0;
 
   if constexpr (!RESIDENT) {
@@ -290,6 +290,7 @@ static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, FwtRevArgs a, bool r
   }
   prof_begin(ctx, resident ? "k_fwt_rev:resident" : "k_fwt_rev:tile", double(a.lines) * a.h0, a.m);
   a.tail = (!resident && ctx->rev_tail && L <= kTailMaxL) ? 1 : 0;
+  a.rot = (a.tail && ctx->rot_warps) ? 1 : 0;
   kern<<<grid, resident ? ctx->res_threads : ctx->rev_threads + 32 * a.tail, smem, ctx->stream>>>(taps, a);
   prof_end(ctx);
   ctx->launches++;

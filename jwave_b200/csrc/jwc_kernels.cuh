@@ -20,6 +20,7 @@ struct FwtFwdArgs {
   int T;                                // tile length (tile mode)
   int G;                                // lines per CTA (resident mode)
   int tiles_per_line, cap0, cap1, tail; // filled in by the launcher
+  int rot;                              // rotate the warps' roles with the CTA number (rotated_tid)
 };
 // Longest filter whose FWT tile kernels get a tail warp: with both steps in one kernel body ptxas hoists
 // the taps of longer filters out of the level loop into vector registers (reverse L = 40: 66 -> 132).
@@ -37,7 +38,7 @@ struct FwtRevArgs {
   int h0, m, T, G;
   RemoteMap rm;                         // mode 2: the output lines go to peer slabs
   // filled in by the launcher
-  int tiles_per_line, ru8, tail;
+  int tiles_per_line, ru8, tail, rot;
   int F[kMaxFuse + 2], g0[kMaxFuse + 1], len[kMaxFuse + 1], offD[kMaxFuse + 1], offA[2];
   int capC, capP[2];
 };
@@ -87,7 +88,7 @@ struct WptFwdArgs {
   int64_t lines;
   int h, m, T, G;
   // filled in by the launcher
-  int tiles_per_line, lg_tpl, lg_T, buf_cap;
+  int tiles_per_line, lg_tpl, lg_T, buf_cap, rot;
   int cap[kMaxFuse + 1];                // tile mode: per-node capacity (double2) of level k
 };
 int wpt_tile_levels(int L, int T, int want, size_t smem_limit, int R);
@@ -100,7 +101,7 @@ struct WptRevArgs {
   int64_t lines;
   int h0, m, T, G;
   // filled in by the launcher
-  int tiles_per_line, lg_tpl, lg_T, ru8, buf_cap;
+  int tiles_per_line, lg_tpl, lg_T, ru8, buf_cap, rot;
   int F[kMaxFuse + 2], g0[kMaxFuse + 1], len[kMaxFuse + 1], cap[kMaxFuse + 1];
 };
 int wpt_rev_tile_levels(int L, int T, int want, size_t smem_limit);

@@ -53,7 +53,7 @@ k_wpt_fwd_tile(const __grid_constant__ Taps taps, const __grid_constant__ WptFwd
   extern __shared__ double2 smem2[];
   constexpr int lgR = (R == 8) ? 3 : 2;
   static_assert(R == 8 || R == 4, "R is 4 or 8");
-  const int tid = threadIdx.x, nthr = blockDim.x, nmain = nthr - 32 * JWC_WPT_TAIL_WARP;
+  const int tid = rotated_tid(a.rot), nthr = blockDim.x, nmain = nthr - 32 * JWC_WPT_TAIL_WARP;
   const int m = a.m, h = a.h, T = a.T;
   const int64_t line = blockIdx.x >> a.lg_tpl;
   const int tile = int(blockIdx.x) & (a.tiles_per_line - 1);
@@ -324,6 +324,7 @@ static cudaError_t launch_LR(jwc_ctx* ctx, const Taps& taps, WptFwdArgs a, bool 
       if (((((1 << (a.m - k)) - 1) * (L - 2)) >> 1) << (k - 1) > 32) inplace = false;
     if (inplace) smem /= 2;
     a.tiles_per_line = a.h / a.T;
+    a.rot = (JWC_WPT_TAIL_WARP && ctx->rot_warps) ? 1 : 0;
     a.lg_tpl = ilog2(a.tiles_per_line);
     a.lg_T = ilog2(a.T);
     grid = a.lines * a.tiles_per_line;

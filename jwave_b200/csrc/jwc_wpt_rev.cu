@@ -63,7 +63,7 @@ k_wpt_rev_tile(const __grid_constant__ Taps taps, const __grid_constant__ WptRev
   extern __shared__ double2 smem2[];
   constexpr int lgRS = (kRS == 8) ? 3 : 2;
   static_assert(kRS == 8 || kRS == 4, "kRS is 4 or 8");
-  const int tid = threadIdx.x, nthr = blockDim.x, nmain = nthr - 32 * JWC_WPT_TAIL_WARP;
+  const int tid = rotated_tid(a.rot), nthr = blockDim.x, nmain = nthr - 32 * JWC_WPT_TAIL_WARP;
   const int m = a.m, h0 = a.h0, T = a.T;
   const int64_t line = blockIdx.x >> a.lg_tpl;
   const int tile = int(blockIdx.x) & (a.tiles_per_line - 1);
@@ -342,6 +342,7 @@ static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, WptRevArgs a, bool r
       if (((a.F[k] >> 1) << (k - 1)) > 32) inplace = false;
     if (inplace) smem /= 2;
     a.tiles_per_line = a.h0 / a.T;
+    a.rot = (JWC_WPT_TAIL_WARP && ctx->rot_warps) ? 1 : 0;
     auto ilog2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
     a.lg_tpl = ilog2(a.tiles_per_line);
     a.lg_T = ilog2(a.T);
