@@ -48,7 +48,7 @@ typedef enum jwc_status {
   JWC_ERR_LEVEL = 2,      /* level outside [0, log2 n] -> JWaveFailure (FastWaveletTransform.java:81-83) */
   JWC_ERR_ARG = 3,        /* null pointer, bad handle, odd filter length, aliasing, ... */
   JWC_ERR_CUDA = 4,       /* a CUDA runtime call failed; see jwc_last_error */
-  JWC_ERR_NCCL = 5        /* reserved: the exchange step of the slab-decomposed 3-D path */
+  JWC_ERR_NCCL = 5        /* reserved (the exchange step of the slab-decomposed 3-D path uses peer copies, not NCCL) */
 } jwc_status;
 
 enum { JWC_FORWARD = 0, JWC_REVERSE = 1 };
@@ -63,6 +63,20 @@ int jwc_version(void);
  * them is one stream at a time per context - jwc_set_stream makes the new stream wait (on the device) for the
  * work enqueued under the previous one, because both use the context's scratch buffers. */
 int jwc_create(jwc_ctx** out, int device);
+/* One context that drives SEVERAL GPUs of the box (1 <= ndev <= 8 distinct CUDA ordinals, peer access between all
+ * pairs): the form SURVEY.md section 8(b) specifies for a single JVM in front of 8 GPUs.  The handle behaves like
+ * a context on devices[0] for every device-resident (*_dev) entry point; the host-buffer entry points use all
+ * devices:
+ *   jwc_fwt1d / jwc_wpt1d / jwc_fwt2d / jwc_wpt2d   the batch is cut into contiguous blocks, one per GPU, each
+ *                                                   through its own staging pipeline (no exchange);
+ *   jwc_fwt3d / jwc_wpt3d                           the volume is slab-decomposed along i when P and Q are
+ *       multiples of ndev (BasicTransform.forward(double[][][]), BasicTransform.java:509-566): k and j passes on
+ *       the owned slices, one re-cut over NVLink on the copy engines, the i pass, and the download scatters the
+ *       result into the reference's layout.  The reverse rebuilds axis i first, as ParallelTransform.reverse does
+ *       (ParallelTransform.java:193) - results differ from the single-device order at rounding level only.
+ * jwc_set_wavelet registers the filters on every device; jwc_destroy releases all of them. */
+int jwc_create_multi(jwc_ctx** out, const int* devices, int ndev);
+int jwc_device_count(const jwc_ctx* ctx);
 int jwc_destroy(jwc_ctx* ctx);
 /* Text of the last failure on this context (never NULL). With ctx == NULL: creation failures. */
 const char* jwc_last_error(const jwc_ctx* ctx);

@@ -23,6 +23,8 @@ _int = C.c_int
 SIGNATURES = {
     "jwc_version": (_int, []),
     "jwc_create": (_int, [C.POINTER(_vp), _int]),
+    "jwc_create_multi": (_int, [C.POINTER(_vp), C.POINTER(_int), _int]),
+    "jwc_device_count": (_int, [_vp]),
     "jwc_destroy": (_int, [_vp]),
     "jwc_last_error": (C.c_char_p, [_vp]),
     "jwc_set_stream": (_int, [_vp, _vp]),

@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <thread>
 
 #include "jwc_internal.cuh"
 #include "jwc_plan.cuh"
@@ -36,6 +37,10 @@ static int fail(jwc_ctx* ctx, int status, const char* msg) {
 }
 
 static void prof_clear(jwc_ctx* ctx);
+static void group_destroy(jwc_ctx* owner);
+static int group_set_wavelet(jwc_ctx* owner, int L, const double* sDe, const double* wDe, const double* sRe,
+                             const double* wRe, int wid);
+static int group_size(const jwc_ctx* ctx);
 
 extern "C" int jwc_version(void) { return JWC_VERSION; }
 
@@ -151,6 +156,7 @@ static void free_scratch(Scratch& s) {
 extern "C" int jwc_destroy(jwc_ctx* ctx) {
   if (!ctx) return JWC_ERR_ARG;
   { JWC_LOCK(ctx); }  // wait for a call still in flight on another thread; the caller must not start new ones
+  if (ctx->group) group_destroy(ctx);
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   prof_clear(ctx);
@@ -287,6 +293,7 @@ extern "C" int jwc_set_wavelet(jwc_ctx* ctx, int L, const double* sDe, const dou
   }
   ctx->wavelets.push_back(rec);
   *wid = int(ctx->wavelets.size()) - 1;
+  if (ctx->group) return group_set_wavelet(ctx, L, sDe, wDe, sRe, wRe, *wid);  // same handle on every device
   return JWC_OK;
 }
 
@@ -710,13 +717,292 @@ static int staged(jwc_ctx* ctx, const double* in, double* out, int64_t items, in
   return status;
 }
 
+
+// ---- device groups: one context that drives several GPUs of the box (jwc_create_multi) ---------------------
+//
+// `jwc_create(out, devices, ndev)` and a `jwc_fwt3d` that slab-shards internally.  One
+// process, one host thread issuing asynchronous work to every GPU, peer access between all pairs
+// (cudaDeviceEnablePeerAccess), events for the cross-device dependencies; no torch, no NCCL.
+//   * batched 1-D / 2-D entry points: the batch is cut into contiguous blocks, one per GPU, each through that
+//     GPU's own staging pipeline on its own host thread - independent signals / images, no exchange;
+//   * jwc_fwt3d / jwc_wpt3d: the volume is slab-decomposed along i.  Forward: every GPU uploads its i-slab in
+//     chunks of slices, runs the k and j passes on a chunk while the next one uploads, and its copy engines
+//     write the chunk's rows into the j-slabs of all GPUs (cudaMemcpy2DAsync, 1 MiB rows); after the re-cut the
+//     i pass runs on the j-slab and the result goes to the host with one strided copy per GPU - the download
+//     IS the second re-cut.  Reverse: mirror image, axis i first (the order of ParallelTransform.reverse,
+//     ParallelTransform.java:193; rounding-level different from BasicTransform.java:602-659).
+struct jwc_group {
+  std::vector<jwc_ctx*> dev;              // dev[0] is the owner context itself
+  std::vector<cudaStream_t> copy;         // one peer-copy stream per device
+  std::vector<Scratch> in, a, b, J, Y;    // per device: i-slab in, two i-slab temporaries, j-slab in / out
+};
+
+static int group_size(const jwc_ctx* ctx) { return (ctx && ctx->group) ? int(ctx->group->dev.size()) : 1; }
+
+extern "C" int jwc_device_count(const jwc_ctx* ctx) { return ctx ? group_size(ctx) : 0; }
+
+static void group_destroy(jwc_ctx* owner) {
+  jwc_group* g = owner->group;
+  owner->group = nullptr;
+  for (size_t i = 0; i < g->dev.size(); ++i) {
+    cudaSetDevice(g->dev[i]->device);
+    cudaDeviceSynchronize();
+    for (auto* v : {&g->in, &g->a, &g->b, &g->J, &g->Y}) free_scratch((*v)[i]);
+    if (g->copy[i]) cudaStreamDestroy(g->copy[i]);
+    if (i > 0) jwc_destroy(g->dev[i]);
+  }
+  delete g;
+}
+
+static int group_set_wavelet(jwc_ctx* owner, int L, const double* sDe, const double* wDe, const double* sRe,
+                             const double* wRe, int wid) {
+  for (size_t i = 1; i < owner->group->dev.size(); ++i) {
+    int w = -1;
+    int st = jwc_set_wavelet(owner->group->dev[i], L, sDe, wDe, sRe, wRe, &w);
+    if (st) return fail(owner, st, jwc_last_error(owner->group->dev[i]));
+    if (w != wid) return fail(owner, JWC_ERR_ARG, "device group: wavelet handles out of step");
+  }
+  return JWC_OK;
+}
+
+extern "C" int jwc_create_multi(jwc_ctx** out, const int* devices, int ndev) {
+  if (!out) return JWC_ERR_ARG;
+  *out = nullptr;
+  auto bad = [&](const std::string& msg, int status) {
+    std::lock_guard<std::mutex> lk(g_create_mu);
+    g_create_err = msg;
+    return status;
+  };
+  if (!devices || ndev < 1 || ndev > 8) return bad("jwc_create_multi: 1 to 8 devices", JWC_ERR_ARG);
+  for (int i = 0; i < ndev; ++i)
+    for (int j = 0; j < i; ++j)
+      if (devices[i] == devices[j]) return bad("jwc_create_multi: duplicate device", JWC_ERR_ARG);
+  jwc_group* g = new jwc_group();
+  int st = JWC_OK;
+  for (int i = 0; i < ndev && !st; ++i) {
+    jwc_ctx* c = nullptr;
+    st = jwc_create(&c, devices[i]);
+    if (!st) g->dev.push_back(c);
+  }
+  for (int i = 0; i < ndev && !st; ++i) {
+    cudaSetDevice(devices[i]);
+    for (int j = 0; j < ndev && !st; ++j) {
+      if (i == j) continue;
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, devices[i], devices[j]);
+      if (!can) st = bad("jwc_create_multi: no peer access between the devices", JWC_ERR_CUDA);
+      else {
+        cudaError_t e = cudaDeviceEnablePeerAccess(devices[j], 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else if (e != cudaSuccess) st = bad(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e), JWC_ERR_CUDA);
+      }
+    }
+  }
+  if (st) {
+    for (auto* c : g->dev) jwc_destroy(c);
+    delete g;
+    return st;
+  }
+  g->copy.assign(ndev, nullptr);
+  for (int i = 0; i < ndev; ++i) {
+    cudaSetDevice(devices[i]);
+    cudaStreamCreateWithFlags(&g->copy[i], cudaStreamNonBlocking);
+  }
+  for (auto* v : {&g->in, &g->a, &g->b, &g->J, &g->Y}) v->resize(ndev);
+  g->dev[0]->group = g;
+  *out = g->dev[0];
+  return JWC_OK;
+}
+
+// batched 1-D / 2-D on a group: contiguous blocks of items, one per GPU, each on its own host thread through
+// that GPU's single-device entry point (independent items: no exchange)
+template <class Call>
+static int group_batch(jwc_ctx* owner, int64_t items, int64_t item_elems, const double* in, double* out, Call call) {
+  jwc_group* g = owner->group;
+  const int nd = int(g->dev.size());
+  std::vector<int> status(nd, JWC_OK);
+  std::vector<std::thread> th;
+  const int64_t base = items / nd, extra = items % nd;
+  int64_t first = 0;
+  for (int i = 0; i < nd; ++i) {
+    const int64_t cnt = base + (i < extra ? 1 : 0);
+    if (cnt > 0 && i > 0) {
+      jwc_ctx* c = g->dev[i];
+      const double* pi = in + first * item_elems;
+      double* po = out + first * item_elems;
+      th.emplace_back([&status, i, c, pi, po, cnt, &call] { status[i] = call(c, pi, po, cnt); });
+    }
+    first += cnt;
+  }
+  // the owner's own block runs on the calling thread, which already holds the owner's (per-thread recursive) lock
+  if (base + (extra > 0 ? 1 : 0) > 0) status[0] = call(g->dev[0], in, out, base + (extra > 0 ? 1 : 0));
+  for (auto& t : th) t.join();
+  for (int i = 0; i < nd; ++i)
+    if (status[i]) return fail(owner, status[i], jwc_last_error(g->dev[i]));
+  return JWC_OK;
+}
+
+#define JWC_G(call)                                                                  \
+  do {                                                                               \
+    cudaError_t e__ = (call);                                                        \
+    if (e__ != cudaSuccess) {                                                        \
+      owner->err = std::string("device group: " #call ": ") + cudaGetErrorString(e__); \
+      return JWC_ERR_CUDA;                                                           \
+    }                                                                                \
+  } while (0)
+
+static int group_axis(jwc_ctx* owner, jwc_ctx* c, int wid, int kind, int dir, const double* in, double* out,
+                      int64_t outer, int n, int64_t inner, int level) {
+  cudaError_t e = cudaSetDevice(c->device);
+  if (e == cudaSuccess) e = run_axis(c, c->wavelets[wid], kind, dir, in, out, outer, n, inner, level);
+  if (e != cudaSuccess) {
+    owner->err = std::string("device group: axis transform: ") + cudaGetErrorString(e);
+    return JWC_ERR_CUDA;
+  }
+  return JWC_OK;
+}
+
+// the slab-decomposed volume; arguments are validated, P and Q are multiples of the group size
+static int group_3d(jwc_ctx* owner, int wid, int kind, int dir, const double* in, double* out, int P, int Q, int R,
+                    int lvlP, int lvlQ, int lvlR) {
+  jwc_group* g = owner->group;
+  const int nd = int(g->dev.size());
+  const int64_t p = P / nd, q = Q / nd;
+  int C = 4;
+  while (C > 1 && p % C) C >>= 1;
+  const int64_t S = p / C;
+  const size_t islab = size_t(p) * Q * R * sizeof(double), jslab = size_t(P) * q * R * sizeof(double);
+  const size_t rowJ = size_t(q) * R * sizeof(double), rowI = size_t(Q) * R * sizeof(double);
+  std::vector<cudaEvent_t> evs;
+  auto new_event = [&](cudaEvent_t* e) {
+    cudaError_t r = cudaEventCreateWithFlags(e, cudaEventDisableTiming);
+    if (r == cudaSuccess) evs.push_back(*e);
+    return r;
+  };
+  struct Cleanup {
+    std::vector<cudaEvent_t>& v;
+    ~Cleanup() { for (auto e : v) cudaEventDestroy(e); }
+  } cleanup{evs};
+  auto ptr = [](Scratch& s) { return static_cast<double*>(s.ptr); };
+  for (int i = 0; i < nd; ++i) {
+    jwc_ctx* c = g->dev[i];
+    JWC_G(cudaSetDevice(c->device));
+    int st;
+    if ((st = ensure(c, g->in[i], islab)) || (st = ensure(c, g->a[i], islab)) || (st = ensure(c, g->b[i], islab)) ||
+        (st = ensure(c, g->J[i], jslab)) || (st = ensure(c, g->Y[i], jslab)))
+      return fail(owner, st, jwc_last_error(c));
+  }
+  std::vector<std::vector<cudaEvent_t>> copied(nd, std::vector<cudaEvent_t>(C));
+  if (dir == JWC_FORWARD) {
+    // BasicTransform.java:509-566 (F5): axis k gets lvlQ, axis j gets lvlP on every slice, then axis i gets lvlR
+    for (int c = 0; c < C; ++c) {
+      for (int i = 0; i < nd; ++i) {
+        jwc_ctx* x = g->dev[i];
+        JWC_G(cudaSetDevice(x->device));
+        const int64_t off = c * S * Q * R;  // chunk c of my i-slab
+        cudaEvent_t up, done;
+        JWC_G(new_event(&up));
+        JWC_G(new_event(&done));
+        JWC_G(new_event(&copied[i][c]));
+        JWC_G(cudaMemcpyAsync(ptr(g->in[i]) + off, in + (int64_t(i) * p + c * S) * Q * R, size_t(S) * Q * R * sizeof(double),
+                              cudaMemcpyHostToDevice, x->h2d_stream));
+        JWC_G(cudaEventRecord(up, x->h2d_stream));
+        JWC_G(cudaStreamWaitEvent(x->own_stream, up, 0));
+        int st;
+        if ((st = group_axis(owner, x, wid, kind, dir, ptr(g->in[i]) + off, ptr(g->a[i]) + off, S * Q, R, 1, lvlQ))) return st;
+        if ((st = group_axis(owner, x, wid, kind, dir, ptr(g->a[i]) + off, ptr(g->b[i]) + off, S, Q, R, lvlP))) return st;
+        JWC_G(cudaEventRecord(done, x->own_stream));
+        JWC_G(cudaStreamWaitEvent(g->copy[i], done, 0));
+        for (int k = 0; k < nd; ++k) {  // my own block first, then round the ring
+          const int d = (i + k) % nd;
+          JWC_G(cudaMemcpy2DAsync(ptr(g->J[d]) + (int64_t(i) * p + c * S) * q * R, rowJ, ptr(g->b[i]) + off + int64_t(d) * q * R,
+                                  rowI, rowJ, size_t(S), cudaMemcpyDefault, g->copy[i]));
+        }
+        JWC_G(cudaEventRecord(copied[i][c], g->copy[i]));
+      }
+    }
+    for (int d = 0; d < nd; ++d) {
+      jwc_ctx* x = g->dev[d];
+      JWC_G(cudaSetDevice(x->device));
+      for (int i = 0; i < nd; ++i)
+        for (int c = 0; c < C; ++c) JWC_G(cudaStreamWaitEvent(x->own_stream, copied[i][c], 0));
+      int st;
+      if ((st = group_axis(owner, x, wid, kind, dir, ptr(g->J[d]), ptr(g->Y[d]), 1, P, q * R, lvlR))) return st;
+      cudaEvent_t done;
+      JWC_G(new_event(&done));
+      JWC_G(cudaEventRecord(done, x->own_stream));
+      JWC_G(cudaStreamWaitEvent(x->d2h_stream, done, 0));
+      // the download is the second re-cut: my j range of every (i, .) row of the host volume
+      JWC_G(cudaMemcpy2DAsync(out + int64_t(d) * q * R, rowI, ptr(g->Y[d]), rowJ, rowJ, size_t(P), cudaMemcpyDeviceToHost,
+                              x->d2h_stream));
+    }
+  } else {
+    // axis i first (ParallelTransform.java:193), then every slice: columns, then rows (BasicTransform.java:611-655)
+    for (int d = 0; d < nd; ++d) {
+      jwc_ctx* x = g->dev[d];
+      JWC_G(cudaSetDevice(x->device));
+      cudaEvent_t up, done;
+      JWC_G(new_event(&up));
+      JWC_G(new_event(&done));
+      JWC_G(cudaMemcpy2DAsync(ptr(g->J[d]), rowJ, in + int64_t(d) * q * R, rowI, rowJ, size_t(P), cudaMemcpyHostToDevice,
+                              x->h2d_stream));
+      JWC_G(cudaEventRecord(up, x->h2d_stream));
+      JWC_G(cudaStreamWaitEvent(x->own_stream, up, 0));
+      int st;
+      if ((st = group_axis(owner, x, wid, kind, dir, ptr(g->J[d]), ptr(g->Y[d]), 1, P, q * R, lvlR))) return st;
+      JWC_G(cudaEventRecord(done, x->own_stream));
+      JWC_G(cudaStreamWaitEvent(g->copy[d], done, 0));
+      for (int c = 0; c < C; ++c) {
+        for (int k = 0; k < nd; ++k) {
+          const int i = (d + k) % nd;
+          JWC_G(cudaMemcpy2DAsync(ptr(g->in[i]) + c * S * Q * R + int64_t(d) * q * R, rowI,
+                                  ptr(g->Y[d]) + (int64_t(i) * p + c * S) * q * R, rowJ, rowJ, size_t(S), cudaMemcpyDefault,
+                                  g->copy[d]));
+        }
+        JWC_G(new_event(&copied[d][c]));
+        JWC_G(cudaEventRecord(copied[d][c], g->copy[d]));
+      }
+    }
+    for (int c = 0; c < C; ++c) {
+      for (int i = 0; i < nd; ++i) {
+        jwc_ctx* x = g->dev[i];
+        JWC_G(cudaSetDevice(x->device));
+        for (int d = 0; d < nd; ++d) JWC_G(cudaStreamWaitEvent(x->own_stream, copied[d][c], 0));
+        const int64_t off = c * S * Q * R;
+        int st;
+        if ((st = group_axis(owner, x, wid, kind, dir, ptr(g->in[i]) + off, ptr(g->a[i]) + off, S, Q, R, lvlP))) return st;
+        if ((st = group_axis(owner, x, wid, kind, dir, ptr(g->a[i]) + off, ptr(g->b[i]) + off, S * Q, R, 1, lvlQ))) return st;
+        cudaEvent_t done;
+        JWC_G(new_event(&done));
+        JWC_G(cudaEventRecord(done, x->own_stream));
+        JWC_G(cudaStreamWaitEvent(x->d2h_stream, done, 0));
+        JWC_G(cudaMemcpyAsync(out + (int64_t(i) * p + c * S) * Q * R, ptr(g->b[i]) + off, size_t(S) * Q * R * sizeof(double),
+                              cudaMemcpyDeviceToHost, x->d2h_stream));
+      }
+    }
+  }
+  for (int i = 0; i < nd; ++i) {
+    jwc_ctx* x = g->dev[i];
+    JWC_G(cudaSetDevice(x->device));
+    JWC_G(cudaStreamSynchronize(x->d2h_stream));
+    JWC_G(cudaStreamSynchronize(g->copy[i]));
+    JWC_G(cudaStreamSynchronize(x->own_stream));
+  }
+  JWC_G(cudaSetDevice(owner->device));
+  return JWC_OK;
+}
+
 static int t1d_host(jwc_ctx* ctx, int wid, int kind, int dir, const double* in, double* out,
-                    int64_t batch, int n, int level) {
+                    int64_t batch, int n, int level, bool sub = false) {
   int st = check_common(ctx, wid, kind, dir, in, out);
   if (st) return st;
   JWC_LOCK(ctx);
   if ((st = check_axis(ctx, n, level))) return st;
   if (batch < 0) return fail(ctx, JWC_ERR_ARG, "negative batch");
+  if (group_size(ctx) > 1 && batch >= group_size(ctx) && !sub)
+    return group_batch(ctx, batch, n, in, out, [=](jwc_ctx* c, const double* pi, double* po, int64_t cnt) {
+      return t1d_host(c, wid, kind, dir, pi, po, cnt, n, level, true);
+    });
   return staged(ctx, in, out, batch, n, [&](const double* di, double* dout, int64_t cnt) {
     return axis_dev(ctx, wid, kind, dir, di, dout, cnt, n, 1, level);
   });
@@ -778,7 +1064,7 @@ extern "C" int jwc_decompose1d(jwc_ctx* ctx, int wid, int kind, const double* in
 }
 
 static int t2d_host(jwc_ctx* ctx, int wid, int kind, int dir, const double* in, double* out,
-                    int64_t batch, int rows, int cols, int lvlM, int lvlN) {
+                    int64_t batch, int rows, int cols, int lvlM, int lvlN, bool sub = false) {
   int st = check_common(ctx, wid, kind, dir, in, out);
   if (st) return st;
   JWC_LOCK(ctx);
@@ -788,6 +1074,10 @@ static int t2d_host(jwc_ctx* ctx, int wid, int kind, int dir, const double* in, 
     if ((st = check_axis(ctx, rows, lvlM)) || (st = check_axis(ctx, cols, lvlN))) return st;
   }
   if (batch < 0) return fail(ctx, JWC_ERR_ARG, "negative batch");
+  if (group_size(ctx) > 1 && batch >= group_size(ctx) && !sub)
+    return group_batch(ctx, batch, int64_t(rows) * cols, in, out, [=](jwc_ctx* c, const double* pi, double* po, int64_t cnt) {
+      return t2d_host(c, wid, kind, dir, pi, po, cnt, rows, cols, lvlM, lvlN, true);
+    });
   return staged(ctx, in, out, batch, int64_t(rows) * cols, [&](const double* di, double* dout, int64_t cnt) {
     return t2d_dev(ctx, wid, kind, dir, di, dout, cnt, rows, cols, lvlM, lvlN);
   });
@@ -808,6 +1098,23 @@ static int t3d_host(jwc_ctx* ctx, int wid, int kind, int dir, const double* in, 
   if (st) return st;
   JWC_LOCK(ctx);
   if (P <= 0 || Q <= 0 || R <= 0) return fail(ctx, JWC_ERR_NOT_BINARY, "given array length is not 2^p | p E N");
+  const int nd = group_size(ctx);
+  if (nd > 1 && P % nd == 0 && Q % nd == 0) {
+    // the same checks, in the same order, as the single-device driver (t3d_dev)
+    if (dir == JWC_FORWARD) {
+      if ((st = check_axis(ctx, R, lvlQ)) || (st = check_axis(ctx, Q, lvlP))) return st;
+    } else {
+      if ((st = check_axis(ctx, Q, lvlP)) || (st = check_axis(ctx, R, lvlQ))) return st;
+    }
+    if ((st = check_axis(ctx, P, lvlR))) return st;
+    if (overlaps(in, out, int64_t(P) * Q * R)) return fail(ctx, JWC_ERR_ARG, "in and out overlap");
+    cudaStream_t user_stream = ctx->stream;
+    if (user_stream != ctx->own_stream) JWC_CUDA(ctx, cudaStreamSynchronize(user_stream));
+    ctx->stream = ctx->own_stream;
+    st = group_3d(ctx, wid, kind, dir, in, out, P, Q, R, lvlP, lvlQ, lvlR);
+    ctx->stream = user_stream;
+    return st;
+  }
   const size_t keep = ctx->staging_bytes;
   ctx->staging_bytes = size_t(-1) / 2;  // one volume is one item
   st = staged(ctx, in, out, 1, int64_t(P) * Q * R, [&](const double* di, double* dout, int64_t) {

@@ -98,7 +98,10 @@ struct Scratch {
 
 }  // namespace jwc
 
+struct jwc_group;  // the devices of a jwc_create_multi context (jwc_capi.cu)
+
 struct jwc_ctx {
+  jwc_group* group = nullptr;  // owner context of a device group: set by jwc_create_multi
   // Every entry point that takes a context holds this lock for its duration: a context is one GPU, one set of
   // scratch buffers and one "current stream", so concurrent callers are serialised here (include/jwave_cuda.h).
   std::recursive_mutex mu;

@@ -37,9 +37,16 @@ class CudaContext:
     _defaults_lock = threading.Lock()
 
     def __init__(self, device=0):
+        """device: a CUDA ordinal, or a list of ordinals for ONE context that drives several GPUs of the box
+        (jwc_create_multi: batched host-buffer calls are sharded over them, a 3-D volume is slab-decomposed)."""
         self._lib = _lib.load()
         handle = C.c_void_p()
-        st = self._lib.jwc_create(C.byref(handle), int(device))
+        if isinstance(device, (list, tuple)):
+            devs = (C.c_int * len(device))(*[int(d) for d in device])
+            st = self._lib.jwc_create_multi(C.byref(handle), devs, len(device))
+            device = device[0] if device else 0
+        else:
+            st = self._lib.jwc_create(C.byref(handle), int(device))
         if st != _lib.OK:
             msg = self._lib.jwc_last_error(None)
             raise JWaveError("jwc_create failed: " + (msg.decode() if msg else f"status {st}"))
@@ -93,6 +100,9 @@ class CudaContext:
 
     def launch_count(self):
         return int(self._lib.jwc_launch_count(self.handle))
+
+    def device_count(self):
+        return int(self._lib.jwc_device_count(self.handle))
 
     def profile(self, on):
         """Bracket every kernel launch with CUDA events (jwc_profile_enable)."""

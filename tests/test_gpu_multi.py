@@ -97,3 +97,44 @@ def test_slab_volume_transform_on_gpus(tmp_path):
     assert np.abs(t_r - ref_r).max() <= 1e-12 * np.abs(ref_f).max()        # i-first order: rounding-level difference
     assert np.abs(t_r - co.parallel_3d(co.FWT, co.REVERSE, "Coiflet5", got_f, *levels)).max() <= 1e-12 * np.abs(ref_f).max()
     assert np.abs(t_g - co.transform_3d(co.FWT, co.FORWARD, "Coiflet5", t_r, *levels)).max() <= 1e-12 * np.abs(t_r).max()
+
+
+def test_device_group_through_the_c_abi():
+    """jwc_create_multi: ONE context, one process, no torch.distributed - the batched host
+    entry points shard over the GPUs and jwc_fwt3d slab-decomposes the volume internally.  Checked against the
+    oracle through the host-side mirror classes, i.e. through ctypes and the C ABI only."""
+    import jwave_b200 as jw
+    from jwave_b200.transforms import CudaContext
+    ndev = min(torch.cuda.device_count(), 4)
+    if ndev < 2:
+        pytest.skip("needs at least 2 GPUs")
+    ctx = CudaContext(list(range(ndev)))
+    assert ctx.device_count() == ndev
+    rng = np.random.default_rng(21)
+    fwt = jw.CudaFastWaveletTransform(jw.WaveletBuilder.create("Coiflet5"), context=ctx)
+    # 3-D: cube, a non-cubic volume with the reference's level shift, and a shape that cannot be slab-cut (falls
+    # back to device 0)
+    for shape, levels in (((64, 64, 64), ()), ((64, 32, 128), (5, 7, 6)), ((8, 8, 16), (3, 4, 3)), ((2, 8, 8), (3, 3, 1))):
+        vol = rng.standard_normal(shape)
+        want = co.transform_3d(co.FWT, co.FORWARD, "Coiflet5", vol, *levels)
+        got = fwt.forward(vol, *levels)
+        assert np.abs(got - want).max() <= 1e-12 * np.abs(vol).max(), shape
+        back = fwt.reverse(want, *levels)   # axis i first on a group: rounding-level difference to the reference order
+        assert np.abs(back - co.transform_3d(co.FWT, co.REVERSE, "Coiflet5", want, *levels)).max() <= 1e-12 * np.abs(want).max()
+    wpt = jw.CudaWaveletPacketTransform(jw.WaveletBuilder.create("Daubechies4"), context=ctx)
+    vol = rng.standard_normal((32, 32, 32))
+    assert np.abs(wpt.forward(vol) - co.transform_3d(co.WPT, co.FORWARD, "Daubechies4", vol)).max() <= 1e-12 * np.abs(vol).max()
+    # batched 1-D and 2-D: contiguous blocks per GPU, including a batch that does not divide evenly
+    x = rng.standard_normal((1001, 512))
+    assert np.abs(fwt.forwardBatch(x) - co.batch_1d(co.FWT, co.FORWARD, "Coiflet5", x, 9)).max() <= 1e-12 * np.abs(x).max()
+    c = co.batch_1d(co.WPT, co.FORWARD, "Daubechies4", x, 4)
+    assert np.abs(wpt.reverseBatch(c, 4) - co.batch_1d(co.WPT, co.REVERSE, "Daubechies4", c, 4)).max() <= 1e-12 * np.abs(c).max()
+    imgs = rng.standard_normal((7, 64, 32))
+    want = np.stack([co.transform_2d(co.FWT, co.FORWARD, "Coiflet5", m) for m in imgs])
+    assert np.abs(fwt.forwardBatch2D(imgs) - want).max() <= 1e-12 * np.abs(imgs).max()
+    # failure classes are those of the single-device path
+    with pytest.raises(jw.JWaveFailure):
+        fwt.forward(rng.standard_normal((64, 48, 64)))
+    with pytest.raises(jw.JWaveFailure):
+        fwt.forward(rng.standard_normal((64, 64, 64)), 7, 6, 6)
+    ctx.close()
