@@ -596,7 +596,62 @@ def run_workload(name, args, env):
                                   "exposed_exchange_ms_per_direction": float(tm[0] - tm[1]),
                                   "nvlink_gbs_sent_per_gpu_copies_alone": nx * xb / (float(tm[2]) * 1e-3) * 1e-9})
 
-    del coef, back
+    group = None
+    if slab is not None and not args.no_e2e:
+        # The same volume through the C ABI's own multi-device form: ONE context over all GPUs of the box
+        # (jwc_create_multi), one process, host buffers in and out - run by rank 0 while the other ranks wait.
+        # This is the e2e of c5 at N > 1 and the driver-visible check of the device group (the test box has 1 GPU).
+        del coef, back
+        coef = back = None
+        torch.cuda.empty_cache()
+        barrier()
+        if rank == 0:
+            try:
+                from jwave_b200.transforms import CudaContext
+                from oracle import c_oracle as co
+                gctx = CudaContext(list(range(world)))
+                gt = jw.CudaFastWaveletTransform(wavelet, context=gctx)
+                rng = np.random.default_rng(77)
+                u, v, w = (rng.standard_normal(n) for _ in range(3))
+                fu, fv, fw = (torch.from_numpy(co.transform_1d(co.FWT, co.FORWARD, cls, t_, level)) for t_ in (u, v, w))
+                hx = torch.empty(n, n, n, dtype=torch.float64).pin_memory()
+                torch.mul(torch.from_numpy(u)[:, None, None] * torch.from_numpy(v)[None, :, None], torch.from_numpy(w)[None, None, :], out=hx)
+                hc = torch.empty_like(hx).pin_memory()
+                hb = torch.empty_like(hx).pin_memory()
+                gl, gh = gctx._lib, gctx.handle
+
+                def gstep():
+                    gctx.check(gl.jwc_fwt3d(gh, gt._wid, _lib.FORWARD, hx.data_ptr(), hc.data_ptr(), n, n, n, level, level, level), "group forward")
+                    gctx.check(gl.jwc_fwt3d(gh, gt._wid, _lib.REVERSE, hc.data_ptr(), hb.data_ptr(), n, n, n, level, level, level), "group reverse")
+                gstep()
+                t0 = time.perf_counter()
+                gstep()
+                gstep()
+                gdt = (time.perf_counter() - t0) / 2
+                # parity of the full volume: rank-one probe against the oracle's three 1-D transforms, plane by plane
+                err = 0.0
+                for i0 in range(0, n, 128):
+                    want = (fu[i0:i0 + 128, None, None] * fv[None, :, None]) * fw[None, None, :]
+                    err = max(err, float((hc[i0:i0 + 128] - want).abs().max()))
+                group = {"value": 2.0 * n ** 3 / gdt * 1e-9, "unit": "GSamples/s", "devices": world,
+                         "ms_per_step": gdt * 1e3, "h2d_bytes_per_step": 2 * 8 * n ** 3, "d2h_bytes_per_step": 2 * 8 * n ** 3,
+                         "api": "jwc_create_multi + jwc_fwt3d (one process, one context, host buffers, pinned)",
+                         "forward_max_err_vs_oracle": err, "tol": 1e-12 * float(hx.abs().max()),
+                         "roundtrip_max_abs_err": float((hb - hx).abs().max())}
+                del hx, hc, hb
+                gctx.close()
+            except Exception as e:
+                group = {"error": f"{type(e).__name__}: {e}"}
+        # the other ranks wait on the HOST (a key in the rendezvous store): an NCCL barrier would park a spinning
+        # kernel on the GPUs rank 0 is using
+        store = dist.distributed_c10d._get_default_store()
+        if rank == 0:
+            store.set(f"group_done_{name}", "1")
+        else:
+            store.wait([f"group_done_{name}"])
+        barrier()
+    else:
+        del coef, back
     if dims == 2:
         del x0
     # ---- e2e: the same step through the host-buffer C ABI, weak-scaled like `value` ----------------------
@@ -675,6 +730,8 @@ def run_workload(name, args, env):
     }
     if slab_info:
         rec["slab"] = slab_info
+    if group:
+        rec["e2e"] = group  # c5 at N > 1: the device group IS the end-to-end path of one volume
     if parity:
         rec["slab_parity"] = parity
         rec["slab_parity_max_err"] = max(parity.get("small_forward_max_err", 0.0), parity.get("small_reverse_max_err", 0.0),
