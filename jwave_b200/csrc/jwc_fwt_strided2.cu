@@ -12,6 +12,7 @@
 #include <cuda.h>
 
 #include <cstring>
+#include <type_traits>
 
 #include "jwc_kernels.cuh"
 #include "jwc_strided2.cuh"
@@ -94,33 +95,47 @@ k_fwt_fwd_str2(const __grid_constant__ Taps taps, const __grid_constant__ FwtFwd
     const int64_t rowD = RESIDENT ? n_det : (h >> k) + int64_t(tile) * n_det;
     const int64_t rowA = RESIDENT ? 0 : int64_t(tile) * n_det;
     if (!RESIDENT || n_det >= R) {
-      const int gkeep = n_det / R;
-      const int groups = RESIDENT ? gkeep : (n_det + ((1 << (m - k)) - 1) * (L - 2) + R - 1) / R;
-      for (int g0 = 0, round = 0; g0 < groups; g0 += ngrp, ++round) {
-        if (k == 1) mbar_wait(&bar[min(round, kStagesF - 1)], 0);
-        const int g = g0 + grp;
-        const bool has = g < groups;
-        double2 lo[R], hi[R];
-        if (has) {
-          const double2* w = X + (2 * R * g) * kL8 + l8;
-          if (g < gkeep) {
-            fwd_run2<L, R, true>(taps, z, [&](int s) { return w[s * kL8]; }, lo, hi);
+      // RR = output rows of one task.  Tile mode: always kR2.  Resident mode: the largest of 4, 2, 1 that still
+      // gives every thread group a task - the short levels at the end of a full-depth transform would otherwise
+      // keep a few threads busy for a whole 4-row task each while the rest of the CTA waits at the barrier
+      // (9 task times for 4 of work on a 256-row line; the resident passes were 27 % of the 1024^3 step).
+      auto level_rounds = [&](auto rc) {
+        constexpr int RR = decltype(rc)::value;
+        const int gkeep = n_det / RR;
+        const int groups = RESIDENT ? gkeep : (n_det + ((1 << (m - k)) - 1) * (L - 2) + RR - 1) / RR;
+        for (int g0 = 0, round = 0; g0 < groups; g0 += ngrp, ++round) {
+          if (k == 1) mbar_wait(&bar[min(round, kStagesF - 1)], 0);
+          const int g = g0 + grp;
+          const bool has = g < groups;
+          double2 lo[RR], hi[RR];
+          if (has) {
+            const double2* w = X + (2 * RR * g) * kL8 + l8;
+            if (g < gkeep) {
+              fwd_run2<L, RR, true>(taps, z, [&](int s) { return w[s * kL8]; }, lo, hi);
 #pragma unroll
-            for (int r = 0; r < R; ++r) st2(pD(rowD + R * g + r), hi[r]);
-            if (last) {
+              for (int r = 0; r < RR; ++r) st2(pD(rowD + RR * g + r), hi[r]);
+              if (last) {
 #pragma unroll
-              for (int r = 0; r < R; ++r) st2(pA(rowA + R * g + r), lo[r]);
+                for (int r = 0; r < RR; ++r) st2(pA(rowA + RR * g + r), lo[r]);
+              }
+            } else {  // halo group (tile mode, never at the last level): low pass only
+              fwd_run2<L, RR, false>(taps, z, [&](int s) { return w[s * kL8]; }, lo, hi);
             }
-          } else {  // halo group (tile mode, never at the last level): low pass only
-            fwd_run2<L, R, false>(taps, z, [&](int s) { return w[s * kL8]; }, lo, hi);
+          }
+          if (last) continue;
+          __syncthreads();  // every window of this round (and of the rounds before it) has been read
+          if (has) {
+#pragma unroll
+            for (int r = 0; r < RR; ++r) X[(RR * g + r) * kL8 + l8] = lo[r];
           }
         }
-        if (last) continue;
-        __syncthreads();  // every window of this round (and of the rounds before it) has been read
-        if (has) {
-#pragma unroll
-          for (int r = 0; r < R; ++r) X[(R * g + r) * kL8 + l8] = lo[r];
-        }
+      };
+      if constexpr (RESIDENT) {
+        if (n_det >= 4 * ngrp) level_rounds(std::integral_constant<int, 4>{});
+        else if (n_det >= 2 * ngrp) level_rounds(std::integral_constant<int, 2>{});
+        else level_rounds(std::integral_constant<int, 1>{});
+      } else {
+        level_rounds(std::integral_constant<int, R>{});
       }
     } else {
       // resident, h_in = 2 or 4: one output row per thread group, true modular wrap
@@ -260,30 +275,39 @@ k_fwt_rev_str2(const __grid_constant__ Taps taps, const __grid_constant__ FwtRev
       const int half = h0 >> k, mask = half - 1;
       const bool last = (k == 1);
       if (half >= R) {
-        const int groups = half / R;
-        auto task = [&](int g, double2 (&t)[2 * R]) {
-          const int top = R * g + R - 1;
-          rev_run2<L, R>(taps, z, [&](int s) { return X[((top - s) & mask) * kL8 + l8]; },
-                         [&](int s) { return X[(half + ((top - s) & mask)) * kL8 + l8]; }, t);
+        // RR = slots of one task: kR2 at the last (largest) level, which loops; at the levels whose results wait in
+        // registers the smallest of 1, 2, 4 that fits the level into one round, so that the short levels at the
+        // start of a full-depth reverse spread over all thread groups (see the forward kernel)
+        auto level = [&](auto rc) {
+          constexpr int RR = decltype(rc)::value;
+          const int groups = half / RR;
+          auto task = [&](int g, double2 (&t)[2 * RR]) {
+            const int top = RR * g + RR - 1;
+            rev_run2<L, RR>(taps, z, [&](int s) { return X[((top - s) & mask) * kL8 + l8]; },
+                            [&](int s) { return X[(half + ((top - s) & mask)) * kL8 + l8]; }, t);
+          };
+          if (!last) {
+            double2 t[2 * RR];
+            const bool has = grp < groups;
+            if (has) task(grp, t);
+            __syncthreads();
+            if (has) {
+#pragma unroll
+              for (int e = 0; e < 2 * RR; ++e) X[(2 * RR * grp + e) * kL8 + l8] = t[e];
+            }
+            __syncthreads();
+          } else {
+            for (int g = grp; g < groups; g += ngrp) {
+              double2 t[2 * RR];
+              task(g, t);
+#pragma unroll
+              for (int e = 0; e < 2 * RR; ++e) st2(pY(2 * RR * g + e), t[e]);
+            }
+          }
         };
-        if (!last) {
-          double2 t[2 * R];
-          const bool has = grp < groups;
-          if (has) task(grp, t);
-          __syncthreads();
-          if (has) {
-#pragma unroll
-            for (int e = 0; e < 2 * R; ++e) X[(2 * R * grp + e) * kL8 + l8] = t[e];
-          }
-          __syncthreads();
-        } else {
-          for (int g = grp; g < groups; g += ngrp) {
-            double2 t[2 * R];
-            task(g, t);
-#pragma unroll
-            for (int e = 0; e < 2 * R; ++e) st2(pY(2 * R * g + e), t[e]);
-          }
-        }
+        if (last || half > 2 * ngrp) level(std::integral_constant<int, 4>{});
+        else if (half > ngrp) level(std::integral_constant<int, 2>{});
+        else level(std::integral_constant<int, 1>{});
       } else {
         // columns of 2 or 4 samples being rebuilt: one slot per thread group, true modular indexing
         double2 t0v = make_double2(0.0, 0.0), t1v = t0v;
