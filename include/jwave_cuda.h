@@ -170,6 +170,11 @@ int jwc_decompose1d_dev(jwc_ctx* ctx, int wid, int kind, const double* in, doubl
 /* device variant: *magnitude_dev (device pointer, may be NULL) receives the mean, no host sync */
 int jwc_compress_magnitude_dev(jwc_ctx* ctx, const double* in, double* out, int64_t count, double threshold,
                                double* magnitude_dev);
+/* Forward transform (kind = JWC_FWT | JWC_WPT) of `batch` signals followed by CompressorMagnitude over ALL
+ * coefficients, in one call: out = compress(forward(in)).  The |c| sum of every 48 MB chunk runs right behind its
+ * transform, out of the L2, so the reduce pass costs no HBM read; the threshold pass is in place.  n % 4 == 0. */
+int jwc_forward1d_compress_dev(jwc_ctx* ctx, int wid, int kind, const double* in, double* out, int64_t batch, int n,
+                               int level, double threshold, double* magnitude_dev);
 /* The building block the 2-D/3-D drivers and the slab-decomposed multi-GPU volume are made of:
  * a dense [outer][n][inner] array, 1-D transform (kind = JWC_FWT | JWC_WPT) along the middle
  * axis of every (outer, inner) line. */

@@ -46,6 +46,7 @@ SIGNATURES = {
     "jwc_decompose1d_dev": (_int, [_vp, _int, _int, _vp, _vp, _i64, _int]),
     "jwc_compress_magnitude": (_int, [_vp, _vp, _vp, _i64, C.c_double, _dp]),
     "jwc_compress_magnitude_dev": (_int, [_vp, _vp, _vp, _i64, C.c_double, _vp]),
+    "jwc_forward1d_compress_dev": (_int, [_vp, _int, _int, _vp, _vp, _i64, _int, _int, C.c_double, _vp]),
     "jwc_fwt1d_dev": (_int, [_vp, _int, _int, _vp, _vp, _i64, _int, _int]),
     "jwc_wpt1d_dev": (_int, [_vp, _int, _int, _vp, _vp, _i64, _int, _int]),
     "jwc_fwt2d_dev": (_int, [_vp, _int, _int, _vp, _vp, _i64, _int, _int, _int, _int]),

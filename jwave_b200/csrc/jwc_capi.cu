@@ -547,6 +547,15 @@ static int decompose_dev(jwc_ctx* ctx, int wid, int kind, const double* in, doub
   if (in < out + batch * sig && out < in + batch * n) return fail(ctx, JWC_ERR_ARG, "in and out overlap");
   JWC_CUDA(ctx, cudaSetDevice(ctx->device));
   const WaveletRec& w = ctx->wavelets[wid];
+  double* D[2] = {nullptr, nullptr};
+  if (kind == JWC_WPT && P > 0) {
+    cudaError_t e0 = ensure_scratch(ctx, 0, size_t(batch) * n * sizeof(double), &D[0]);
+    if (e0 == cudaSuccess) e0 = ensure_scratch(ctx, 1, size_t(batch) * n * sizeof(double), &D[1]);
+    if (e0 != cudaSuccess) {
+      ctx->err = std::string("decompose: ") + cudaGetErrorString(e0);
+      return JWC_ERR_CUDA;
+    }
+  }
   JWC_CUDA(ctx, cudaMemcpy2DAsync(out, size_t(sig) * sizeof(double), in, size_t(n) * sizeof(double),
                                   size_t(n) * sizeof(double), size_t(batch), cudaMemcpyDeviceToDevice, ctx->stream));
   for (int p = 0; p < P; ++p) {
@@ -566,19 +575,24 @@ static int decompose_dev(jwc_ctx* ctx, int wid, int kind, const double* in, doub
                               size_t(sig) * sizeof(double), size_t(n - h) * sizeof(double), size_t(batch),
                               cudaMemcpyDeviceToDevice, ctx->stream);
     } else {
-      for (int64_t b = 0; b < batch && e == cudaSuccess; ++b) {  // 2^p packets of width h per signal
-        a.src = out + b * sig + int64_t(p) * n;        a.src_os = h;
-        a.dstA = out + b * sig + int64_t(p + 1) * n;   a.dstA_os = h;
-        a.dstD = a.dstA + h / 2;                       a.dstD_os = h;
-        a.outer = int64_t(1) << p;
-        e = launch_fwd_level_generic(ctx, w.L, w.de, a);
-      }
+      // every signal's 2^p packets of width h in ONE launch: level p runs dense [batch][n] -> dense [batch][n]
+      // (batch * 2^p lines of stride h) between two scratch arrays, and the new row is copied into out[b][p + 1]
+      const double* src = (p == 0) ? in : D[p & 1];
+      a.src = src;                    a.src_os = h;
+      a.dstA = D[(p + 1) & 1];        a.dstA_os = h;
+      a.dstD = a.dstA + h / 2;        a.dstD_os = h;
+      a.outer = batch << p;
+      e = launch_fwd_level_generic(ctx, w.L, w.de, a);
+      if (e == cudaSuccess)
+        e = cudaMemcpy2DAsync(out + int64_t(p + 1) * n, size_t(sig) * sizeof(double), D[(p + 1) & 1], size_t(n) * sizeof(double),
+                              size_t(n) * sizeof(double), size_t(batch), cudaMemcpyDeviceToDevice, ctx->stream);
     }
     if (e != cudaSuccess) {
       ctx->err = std::string("decompose: ") + cudaGetErrorString(e);
       return JWC_ERR_CUDA;
     }
   }
+  mark_scratch(ctx);
   return JWC_OK;
 }
 
@@ -590,6 +604,18 @@ extern "C" int jwc_decompose1d_dev(jwc_ctx* ctx, int wid, int kind, const double
   return decompose_dev(ctx, wid, kind, in, out, batch, n);
 }
 
+// scratch of the compressor kernels: blocks partial sums, the magnitude, the CTA counter (zero between calls)
+static int compress_scratch(jwc_ctx* ctx, int blocks, double** scratch) {
+  const size_t need = size_t(blocks + 2) * sizeof(double);
+  if (ctx->scratch[3].bytes < need) {
+    int st = ensure(ctx, ctx->scratch[3], need);
+    if (st) return st;
+    JWC_CUDA(ctx, cudaMemsetAsync(ctx->scratch[3].ptr, 0, need, ctx->stream));
+  }
+  *scratch = static_cast<double*>(ctx->scratch[3].ptr);
+  return JWC_OK;
+}
+
 // CompressorMagnitude on device-resident coefficients; the magnitude stays on the device
 static int compress_dev(jwc_ctx* ctx, const double* in, double* out, int64_t count, double threshold,
                         double* magnitude_dev) {
@@ -598,12 +624,57 @@ static int compress_dev(jwc_ctx* ctx, const double* in, double* out, int64_t cou
   if (!in || !out) return fail(ctx, JWC_ERR_ARG, "null data pointer");
   if (!(threshold > 0.)) return fail(ctx, JWC_ERR_ARG, "Compressor - given threshold should be larger than zero!");
   if (count < 1) return fail(ctx, JWC_ERR_ARG, "Compressor - empty array");
+  if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 31)
+    return fail(ctx, JWC_ERR_ARG, "Compressor - device arrays must be 32-byte aligned");
   JWC_CUDA(ctx, cudaSetDevice(ctx->device));
   const int blocks = ctx->sm_count * 8;
-  int st = ensure(ctx, ctx->scratch[3], size_t(blocks + 1) * sizeof(double));
+  double* scratch = nullptr;
+  int st = compress_scratch(ctx, blocks, &scratch);
   if (st) return st;
-  double* scratch = static_cast<double*>(ctx->scratch[3].ptr);
   cudaError_t e = launch_compress_magnitude(ctx, in, out, count, threshold, scratch, blocks);
+  mark_scratch(ctx);
+  if (e != cudaSuccess) {
+    ctx->err = std::string("compress: ") + cudaGetErrorString(e);
+    return JWC_ERR_CUDA;
+  }
+  if (magnitude_dev)
+    JWC_CUDA(ctx, cudaMemcpyAsync(magnitude_dev, scratch + blocks, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  return JWC_OK;
+}
+
+// Forward transform + CompressorMagnitude in one call (the compression use case: Compressor.java:97-110 applied to
+// the output of FastWaveletTransform / WaveletPacketTransform.forward).  The magnitude is a mean over ALL
+// coefficients, so the threshold pass cannot start before the last coefficient exists; what CAN be saved is the
+// read of the reduce pass: the batch is transformed in chunks of at most 48 MB and the |c| sum of a chunk runs
+// right behind its forward transform, while the chunk still sits in the 126 MB L2.  HBM traffic per coefficient:
+// 16 B (transform) + 16 B (threshold, in place) instead of + 8 B for a separate reduce.
+extern "C" int jwc_forward1d_compress_dev(jwc_ctx* ctx, int wid, int kind, const double* in, double* out, int64_t batch,
+                                          int n, int level, double threshold, double* magnitude_dev) {
+  int st = check_common(ctx, wid, kind, JWC_FORWARD, in, out);
+  if (st) return st;
+  JWC_LOCK(ctx);
+  if ((st = check_axis(ctx, n, level))) return st;
+  if (!(threshold > 0.)) return fail(ctx, JWC_ERR_ARG, "Compressor - given threshold should be larger than zero!");
+  if (batch < 1) return fail(ctx, JWC_ERR_ARG, "Compressor - empty array");
+  if ((reinterpret_cast<uintptr_t>(out) & 31) || (n & 3)) return fail(ctx, JWC_ERR_ARG, "Compressor - n % 4 == 0 and 32-byte aligned arrays");
+  if (overlaps(in, out, batch * n)) return fail(ctx, JWC_ERR_ARG, "in and out overlap");
+  JWC_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int blocks = ctx->sm_count * 8;
+  double* scratch = nullptr;
+  if ((st = compress_scratch(ctx, blocks, &scratch))) return st;
+  int64_t chunk = (int64_t(48) << 20) / (int64_t(n) * int64_t(sizeof(double)));
+  if (chunk < 1) chunk = 1;
+  const int64_t total = batch * n;
+  for (int64_t first = 0; first < batch; first += chunk) {
+    const int64_t cnt = batch - first < chunk ? batch - first : chunk;
+    if ((st = axis_dev(ctx, wid, kind, JWC_FORWARD, in + first * n, out + first * n, cnt, n, 1, level))) return st;
+    cudaError_t e = launch_abs_sum(ctx, out + first * n, cnt * n, total, scratch, blocks, first > 0, first + cnt >= batch);
+    if (e != cudaSuccess) {
+      ctx->err = std::string("compress: ") + cudaGetErrorString(e);
+      return JWC_ERR_CUDA;
+    }
+  }
+  cudaError_t e = launch_threshold(ctx, out, out, total, threshold, scratch, blocks);
   mark_scratch(ctx);
   if (e != cudaSuccess) {
     ctx->err = std::string("compress: ") + cudaGetErrorString(e);
@@ -641,7 +712,7 @@ extern "C" int jwc_compress_magnitude(jwc_ctx* ctx, const double* in, double* ou
   if (!st) {
     e = cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess && magnitude)
-      e = cudaMemcpyAsync(magnitude, static_cast<double*>(ctx->scratch[3].ptr) + ctx->sm_count * 8, sizeof(double),
+      e = cudaMemcpyAsync(magnitude, static_cast<double*>(ctx->scratch[3].ptr) + ctx->sm_count * 8 /* = blocks */, sizeof(double),
                           cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) st = JWC_ERR_CUDA;

@@ -177,8 +177,14 @@ struct RevLevelArgs {
 cudaError_t launch_fwd_level_generic(jwc_ctx* ctx, int L, const Taps& taps, const FwdLevelArgs& a);
 cudaError_t launch_rev_level_generic(jwc_ctx* ctx, int L, const Taps& taps, const RevLevelArgs& a);
 
-// jwc_compress.cu: CompressorMagnitude; `scratch` holds blocks + 1 doubles (partials, magnitude)
+// jwc_compress.cu: CompressorMagnitude; `scratch` holds blocks + 2 doubles (partials, magnitude, CTA counter = 0)
 cudaError_t launch_compress_magnitude(jwc_ctx* ctx, const double* in, double* out, int64_t n, double threshold,
                                       double* scratch, int blocks);
+// the two halves: |x| partial sums (optionally accumulated over several calls; `finish` = also write the mean over
+// n_total) and the threshold pass; scratch holds blocks + 2 doubles, zero-initialised
+cudaError_t launch_abs_sum(jwc_ctx* ctx, const double* in, int64_t n, int64_t n_total, double* scratch, int blocks,
+                           bool accumulate, bool finish);
+cudaError_t launch_threshold(jwc_ctx* ctx, const double* in, double* out, int64_t n, double threshold, double* scratch,
+                             int blocks);
 
 }  // namespace jwc

@@ -94,6 +94,18 @@ class DeviceTransforms:
         self.ctx.check(st, "jwc_3d_dev")
         return out
 
+    def forward_compress1d(self, kind, x, level, threshold, out=None):
+        """jwc_forward1d_compress_dev: CompressorMagnitude(threshold).compress(forward(x)) for a [batch][n] tensor in one
+        call (Compressor.java:97-110 behind FastWaveletTransform / WaveletPacketTransform.forward); returns
+        (coefficients with the small ones zeroed, magnitude as a 1-element device tensor)."""
+        x, out = self._prep(x, out)
+        n = x.shape[-1]
+        mag = torch.empty(1, dtype=torch.float64, device=self.device)
+        st = self._L.jwc_forward1d_compress_dev(self.ctx.handle, self.wid, kind, x.data_ptr(), out.data_ptr(),
+                                                x.numel() // n, n, level, float(threshold), mag.data_ptr())
+        self.ctx.check(st, "jwc_forward1d_compress_dev")
+        return out, mag
+
     def copy2d(self, dst, dpitch, src, spitch, width, height, stream=None):
         """jwc_copy2d_dev: strided device copy on the copy engines; dst / src are device pointers (ints), pitches
         and width in bytes; `stream` a torch stream (default: the current one)."""

@@ -305,6 +305,31 @@ def test_compressor_magnitude():
     assert jw.CompressorMagnitude(-3.0).getThreshold() == 1.0  # Compressor.java:52-66
 
 
+@pytest.mark.parametrize("kind", ["fwt", "wpt"])
+def test_forward_and_compress_in_one_call(kind):
+    """jwc_forward1d_compress_dev == CompressorMagnitude.compress(forward(x)): the |c| sum runs chunk by chunk behind
+    the transform (several chunks here: 48 MB each), the threshold pass in place."""
+    import torch
+    from jwave_b200.device import DeviceTransforms
+    cls, n, level, batch = "Daubechies4", 4096, (12 if kind == "fwt" else 5), 4000   # 125 MB of coefficients
+    dev = DeviceTransforms(jw.WaveletBuilder.create(cls))
+    x = rng_signal(123, batch, n)
+    K = _lib.FWT if kind == "fwt" else _lib.WPT
+    xd = torch.from_numpy(x).cuda()
+    got, mag = dev.forward_compress1d(K, xd, level, 0.8)
+    c = co.batch_1d(okind(kind), co.FORWARD, cls, x, level)
+    ref, rmag = co.compress_magnitude(c, 0.8)
+    assert abs(float(mag) - rmag) <= 1e-12 * rmag
+    g = got.cpu().numpy()
+    safe = np.abs(np.abs(c) - rmag * 0.8) > 1e-11 * rmag
+    kept = ref != 0.0
+    assert np.array_equal((g != 0.0)[safe], kept[safe])
+    assert np.abs(g[safe & kept] - ref[safe & kept]).max() <= 1e-12 * np.abs(x).max()
+    again, mag2 = dev.forward_compress1d(K, xd, level, 0.8)   # the CTA counter is back at zero: same result
+    assert torch.equal(again, got) and float(mag2) == float(mag)
+    dev.close()
+
+
 def test_abi_status_codes():
     """Raw C-ABI status codes (include/jwave_cuda.h) without the Python pre-checks."""
     import ctypes as C
