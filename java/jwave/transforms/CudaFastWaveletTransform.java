@@ -5,6 +5,8 @@
  *   Transform t = new Transform( new CudaFastWaveletTransform( new Daubechies4( ) ) );
  *   double[ ] hilb = t.forward( arrTime );       // Transform.java:81
  *   double[ ] reco = t.reverse( hilb );
+ *
+ * new CudaFastWaveletTransform( wavelet, 0, 1, 2, 3, 4, 5, 6, 7 ) puts all eight GPUs of a box behind the one object.
  */
 package jwave.transforms;
 
@@ -18,8 +20,8 @@ public class CudaFastWaveletTransform extends CudaWaveletTransform {
     this( wavelet, 0 );
   }
 
-  public CudaFastWaveletTransform( Wavelet wavelet, int device ) throws JWaveException {
-    super( wavelet, JWaveCuda.FWT, "FastWaveletTransform", device );
-    _name = "Fast Wavelet Transform"; // FastWaveletTransform.java:51
+  public CudaFastWaveletTransform( Wavelet wavelet, int... devices ) throws JWaveException {
+    super( wavelet, JWaveCuda.FWT, "FastWaveletTransform", devices );
+    _name = "Fast Wavelet Transform";
   }
 }

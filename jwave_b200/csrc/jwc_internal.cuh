@@ -131,8 +131,7 @@ struct jwc_ctx {
   int str_tile = 512, str_rev_tile = 512, str_rev_m = 5, str_cap = 512, str_threads = 128, str_rev_threads = 128, str_tma = 1;  // strided-axis kernels
   // second-generation strided kernels (inner % 16 == 0): on/off, tile rows, resident cap, forced levels per pass (0 = halo rule)
   int rot_warps = 0;  // tile kernels with a tail warp: rotate the warps' roles with the CTA number (rotated_tid; measured slower)
-  int fuse_tail = 1;  // contiguous FWT: small trailing / leading passes share one launch where the kernels allow
-  int str_v2 = 1, str2_tile = 512, str2_rev_tile = 512, str2_cap = 512, str2_m = 0, str2_rev_m = 0;
+  int str_v2 = 1, str2_tile = 512, str2_rev_tile = 256 /* A/B: profiles/r02_ab_strided_v2_tuning.txt */, str2_cap = 512, str2_m = 0, str2_rev_m = 0;
 };
 
 namespace jwc {
