@@ -111,7 +111,7 @@ extern "C" int jwc_create(jwc_ctx** out, int device) {
         {"str2_tile", &ctx->str2_tile, true, 128, 1 << 12},   {"str2_rev_tile", &ctx->str2_rev_tile, true, 128, 1 << 12},
         {"str2_cap", &ctx->str2_cap, true, 16, 1 << 11},      {"str2_m", &ctx->str2_m, false, 0, 8},
         {"str2_rev_m", &ctx->str2_rev_m, false, 0, 8},
-        {"rot_warps", &ctx->rot_warps, false, 0, 1},
+        {"rot_warps", &ctx->rot_warps, false, 0, 1},               {"shfl", &ctx->shfl, false, 0, 1},
     };
     std::string bad;
     const char* p = tune;

@@ -27,6 +27,8 @@ struct FwtFwdArgs {
 constexpr int kTailMaxL = 24;
 int fwt_tile_levels(int L, int T);
 cudaError_t launch_fwt_fwd(jwc_ctx* ctx, int L, const Taps& taps, const FwtFwdArgs& a, bool resident);
+// jwc_shfl.cu: 2-tap filters, registers + warp shuffles, up to 8 levels per launch (cudaErrorNotSupported = declined)
+cudaError_t launch_fwt_fwd_shfl(jwc_ctx* ctx, int L, const Taps& taps, const FwtFwdArgs& a);
 
 // ---- reverse FWT, contiguous lines (jwc_fwt_rev.cu) -----------------------------------------
 constexpr int kMaxFuse = 12;

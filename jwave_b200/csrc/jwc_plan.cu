@@ -197,7 +197,7 @@ static cudaError_t fwt_forward(jwc_ctx* ctx, const WaveletRec& w, const double* 
   if (ctx->remote) return cudaErrorNotSupported;  // peer stores exist in the strided forward kernels only
   if (!w.mirror_de || !fused_ok(ctx, in, out, n, inner)) return fwt_forward_generic(ctx, w, in, out, outer, n, inner, level);
   const int cap = ctx->res_cap;
-  struct Pass { int h, T, m; bool resident; };
+  struct Pass { int h, T, m; bool resident, shfl; };
   Pass passes[32];
   int npass = 0;
   size_t need[2] = {0, 0};
@@ -206,7 +206,11 @@ static cudaError_t fwt_forward(jwc_ctx* ctx, const WaveletRec& w, const double* 
     p.h = h;
     p.resident = (h <= cap);
     p.T = p.resident ? h : (h < ctx->fwd_tile ? h : ctx->fwd_tile);
-    if (p.resident) {
+    // 2-tap filters: up to 8 levels per launch in registers and warp shuffles (jwc_shfl.cu) instead of a tile pass
+    p.shfl = ctx->shfl && w.L == 2 && !p.resident && h % 256 == 0;
+    if (p.shfl) {
+      p.m = left < 8 ? left : 8;
+    } else if (p.resident) {
       p.m = left;
     } else {
       int m_tile = fwt_tile_levels(w.L, p.T);
@@ -234,7 +238,15 @@ static cudaError_t fwt_forward(jwc_ctx* ctx, const WaveletRec& w, const double* 
     a.G = p.resident ? resident_lines(p.h, 150) : 1;   // fwd: (h/2 + h/4) double2, padded 1.25
     a.dstA = last ? out : S[(i + 1) & 1];
     a.dstA_os = last ? n : (p.h >> p.m);
-    JWC_TRY(launch_fwt_fwd(ctx, w.L, w.de, a, p.resident));
+    cudaError_t e = p.shfl ? launch_fwt_fwd_shfl(ctx, w.L, w.de, a) : cudaErrorNotSupported;
+    if (e == cudaErrorNotSupported) {
+      if (p.shfl) {  // declined (alignment): the tile kernel takes the same pass if it can fuse that many levels
+        int m_tile = fwt_tile_levels(w.L, p.T);
+        if (p.m > m_tile) return cudaErrorInvalidValue;
+      }
+      e = launch_fwt_fwd(ctx, w.L, w.de, a, p.resident);
+    }
+    JWC_TRY(e);
     a.src = a.dstA; a.src_os = a.dstA_os;
   }
   return cudaSuccess;
