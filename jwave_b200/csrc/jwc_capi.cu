@@ -112,6 +112,8 @@ extern "C" int jwc_create(jwc_ctx** out, int device) {
         {"str2_cap", &ctx->str2_cap, true, 16, 1 << 11},      {"str2_m", &ctx->str2_m, false, 0, 8},
         {"str2_rev_m", &ctx->str2_rev_m, false, 0, 8},
         {"rot_warps", &ctx->rot_warps, false, 0, 1},               {"shfl", &ctx->shfl, false, 0, 1},
+        {"carve", &ctx->carve, false, 0, 1},                     {"xsmem", &ctx->xsmem, false, 0, 200},
+        {"stagger", &ctx->stagger, false, 0, 100000},              {"res_kb", &ctx->res_kb, false, 4, 200},
     };
     std::string bad;
     const char* p = tune;

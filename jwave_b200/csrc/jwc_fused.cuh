@@ -22,6 +22,22 @@ __device__ __forceinline__ int rotated_tid(int rot) {
   return int((((w + blockIdx.x) % nw) << 5) | (threadIdx.x & 31));
 }
 
+// First-wave stagger (JWC_TUNE stagger=ns; OFF by default).  Every CTA of a tile kernel lives equally long and a new
+// one starts when an old one retires, so the phase pattern of the first wave - all resident CTAs of an SM staging at
+// once, then all in their FMA phase at once - can persist through the launch.  With the switch on, CTA b of the first
+// wave (b < ctas) waits ((b / div) mod 8) * ns before it starts: div = SM count, i.e. the k-th CTA an SM receives.
+__device__ __forceinline__ void first_wave_stagger(int ns, int ctas, int div) {
+  if (ns > 0 && int(blockIdx.x) < ctas) {
+    const unsigned wait = unsigned((blockIdx.x / unsigned(div)) & 7) * unsigned(ns);
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do {
+      __nanosleep(200);
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    } while (t1 - t0 < wait);
+  }
+}
+
 // Padded shared-memory layout of a line segment: interleaved samples as double2 (x[2k], x[2k+1]), one
 // pad slot after every 4 double2.  A thread that produces outputs 4g..4g+3 reads the window
 // k = 4g .. 4g + L/2 + 2; consecutive threads are 5 slots (80 B) apart, so the 8 lanes of a

@@ -195,6 +195,7 @@ static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, FwtFwdArgs a, bool r
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
   }
+  if (ctx->carve) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   prof_begin(ctx, resident ? "k_fwt_fwd:resident" : "k_fwt_fwd:tile", double(a.lines) * a.h, a.m);
   a.tail = (!resident && ctx->fwd_tail && L <= kTailMaxL) ? 1 : 0;
   a.rot = (a.tail && ctx->rot_warps) ? 1 : 0;

@@ -288,6 +288,7 @@ static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, FwtRevArgs a, bool r
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
   }
+  if (ctx->carve) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   prof_begin(ctx, resident ? "k_fwt_rev:resident" : "k_fwt_rev:tile", double(a.lines) * a.h0, a.m);
   a.tail = (!resident && ctx->rev_tail && L <= kTailMaxL) ? 1 : 0;
   a.rot = (a.tail && ctx->rot_warps) ? 1 : 0;

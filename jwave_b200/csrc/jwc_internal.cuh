@@ -130,6 +130,10 @@ struct jwc_ctx {
   int fwd_tile = 2048, fwd_m = 4 /* cap on the halo rule */, fwd_r = 4, rev_tile = 4096, rev_m = 3, rev_rs = 4, fwd_threads = 128, rev_threads = 128, res_cap = 256, res_threads = 128, wpt_tile = 2048, wpt_m = 3, wpt_threads = 160, wpt_rs = 8, wpt_r = 8, wpt_inplace = 1, rev_tail = 1, fwd_tail = 1;
   int str_tile = 512, str_rev_tile = 512, str_rev_m = 5, str_cap = 512, str_threads = 128, str_rev_threads = 128, str_tma = 1;  // strided-axis kernels
   // second-generation strided kernels (inner % 16 == 0): on/off, tile rows, resident cap, forced levels per pass (0 = halo rule)
+  int res_kb = 48;    // resident kernels: shared-memory budget per CTA (KB) that sets the lines per CTA
+  int stagger = 0;    // WPT tile kernels: first-wave stagger in ns per resident-CTA slot (jwc_fused.cuh)
+  int xsmem = 0;      // extra dynamic shared memory (KB) per CTA of the WPT tile kernels: an A/B knob that LOWERS the CTAs per SM
+  int carve = 0;      // tile kernels: ask for the largest shared-memory carve-out (A/B: does the driver's choice cap the CTAs per SM?)
   int shfl = 1;       // 2-tap filters, forward FWT: the register / warp-shuffle kernel (jwc_shfl.cu) instead of tile passes
   int rot_warps = 0;  // tile kernels with a tail warp: rotate the warps' roles with the CTA number (rotated_tid; measured slower)
   int str_v2 = 1, str2_tile = 512, str2_rev_tile = 256 /* A/B: profiles/r02_ab_strided_v2_tuning.txt */, str2_cap = 512, str2_m = 0, str2_rev_m = 0;

@@ -5,8 +5,10 @@
 namespace jwc {
 
 // every even filter length in scope: Haar1 (2) .. Daubechies20 / Symlet20 (40)
+#ifndef JWC_FOR_EACH_L
 #define JWC_FOR_EACH_L(X) \
   X(2) X(4) X(6) X(8) X(10) X(12) X(14) X(16) X(18) X(20) X(22) X(24) X(26) X(28) X(30) X(32) X(34) X(36) X(38) X(40)
+#endif
 
 
 // ---- forward FWT, contiguous lines (jwc_fwt_fwd.cu) -----------------------------------------
@@ -91,6 +93,7 @@ struct WptFwdArgs {
   int h, m, T, G;
   // filled in by the launcher
   int tiles_per_line, lg_tpl, lg_T, buf_cap, rot;
+  int stagger_ns, stagger_ctas, stagger_div;  // first-wave stagger (A/B switch, jwc_fused.cuh)
   int cap[kMaxFuse + 1];                // tile mode: per-node capacity (double2) of level k
 };
 int wpt_tile_levels(int L, int T, int want, size_t smem_limit, int R);
@@ -104,6 +107,9 @@ struct WptRevArgs {
   int h0, m, T, G;
   // filled in by the launcher
   int tiles_per_line, lg_tpl, lg_T, ru8, buf_cap, rot;
+  int stagger_ns, stagger_ctas, stagger_div;  // first-wave stagger (A/B switch, jwc_fused.cuh)
+  int stage_left, stage_len2, cap_m;    // tile mode, staging: F[m] + ru8, len[m] / 2, cap[m]
+  unsigned geo; int geo_ok;             // tile mode: capB | Fx << 16 | ru8 << 22 | lg T << 27 (jwc_wpt_rev.cu)
   int F[kMaxFuse + 2], g0[kMaxFuse + 1], len[kMaxFuse + 1], cap[kMaxFuse + 1];
 };
 int wpt_rev_tile_levels(int L, int T, int want, size_t smem_limit);

@@ -45,9 +45,9 @@ static cudaError_t copy_through(jwc_ctx* ctx, const double* in, double* out, int
 
 // Lines per CTA in resident mode: as many as fit a shared-memory budget that keeps ~4 CTAs per SM,
 // so short lines (the tail of every full-depth transform) still fill the CTA's threads.
-static int resident_lines(int h, int bytes_per_sample_x10) {
+static int resident_lines(const jwc_ctx* ctx, int h, int bytes_per_sample_x10) {
   const int64_t per_line = int64_t(h) * bytes_per_sample_x10 / 10 + 64;
-  int64_t g = (48 * 1024) / per_line;
+  int64_t g = (int64_t(ctx->res_kb) * 1024) / per_line;
   if (g < 1) g = 1;
   if (g > 64) g = 64;
   return int(g);
@@ -210,6 +210,9 @@ static cudaError_t fwt_forward(jwc_ctx* ctx, const WaveletRec& w, const double* 
     p.shfl = ctx->shfl && w.L == 2 && !p.resident && h % 256 == 0;
     if (p.shfl) {
       p.m = left < 8 ? left : 8;
+      // a_m of a pass that is not the last one goes to compact lines of h >> m samples, which the next pass reads
+      // with 32-byte loads: keep them at least 4 samples wide (h = 256, 9 levels to go: 6 + 3, not 8 + 1)
+      while (p.m < left && (h >> p.m) < 4) --p.m;
     } else if (p.resident) {
       p.m = left;
     } else {
@@ -235,7 +238,7 @@ static cudaError_t fwt_forward(jwc_ctx* ctx, const WaveletRec& w, const double* 
     const Pass& p = passes[i];
     const bool last = (i == npass - 1);
     a.h = p.h; a.T = p.T; a.m = p.m;
-    a.G = p.resident ? resident_lines(p.h, 150) : 1;   // fwd: (h/2 + h/4) double2, padded 1.25
+    a.G = p.resident ? resident_lines(ctx, p.h, 150) : 1;   // fwd: (h/2 + h/4) double2, padded 1.25
     a.dstA = last ? out : S[(i + 1) & 1];
     a.dstA_os = last ? n : (p.h >> p.m);
     cudaError_t e = p.shfl ? launch_fwt_fwd_shfl(ctx, w.L, w.de, a) : cudaErrorNotSupported;
@@ -332,7 +335,7 @@ static cudaError_t fwt_reverse(jwc_ctx* ctx, const WaveletRec& w, const double* 
     const bool last = (p.h0 == n);
     a.h0 = p.h0; a.m = p.m;
     a.T = (p.resident || p.h0 < ctx->rev_tile) ? p.h0 : ctx->rev_tile;
-    a.G = p.resident ? resident_lines(p.h0, 140) : 1;  // rev: (h + h/2 + h/4) samples, unpadded
+    a.G = p.resident ? resident_lines(ctx, p.h0, 140) : 1;  // rev: (h + h/2 + h/4) samples, unpadded
     a.dst = last ? out : S[i & 1];
     a.dst_os = last ? n : p.h0;
     a.rm = (last && ctx->remote) ? *ctx->remote : RemoteMap();
@@ -416,7 +419,7 @@ static cudaError_t wpt_forward(jwc_ctx* ctx, const WaveletRec& w, const double* 
     a.lines = outer * (n / p.h);
     a.h = p.h; a.m = p.m;
     a.T = (p.resident || p.h < ctx->wpt_tile) ? p.h : ctx->wpt_tile;
-    a.G = p.resident ? resident_lines(p.h, 200) : 1;   // wpt: two full line buffers, padded 1.25
+    a.G = p.resident ? resident_lines(ctx, p.h, 200) : 1;   // wpt: two full line buffers, padded 1.25
     JWC_TRY(launch_wpt_fwd(ctx, w.L, w.de, a, p.resident));
     src = a.dst;
   }
@@ -462,7 +465,7 @@ static cudaError_t wpt_reverse(jwc_ctx* ctx, const WaveletRec& w, const double* 
     a.lines = outer * (n / p.h0);
     a.h0 = p.h0; a.m = p.m;
     a.T = (p.resident || p.h0 < ctx->wpt_tile) ? p.h0 : ctx->wpt_tile;
-    a.G = p.resident ? resident_lines(p.h0, 200) : 1;
+    a.G = p.resident ? resident_lines(ctx, p.h0, 200) : 1;
     JWC_TRY(launch_wpt_rev(ctx, w.L, w.re, a, p.resident));
     src = a.dst;
   }

@@ -26,6 +26,14 @@
 
 namespace jwc {
 
+// Launch bound of the tile kernels.  -DJWC_WPT_MINB=n builds them for 160-thread CTAs with n CTAs per SM (an A/B
+// switch for the register budget; the default keeps run-time CTA sizes up to 512).
+#ifdef JWC_WPT_MINB
+#define JWC_WPT_TILE_BOUNDS __launch_bounds__(160, JWC_WPT_MINB)
+#else
+#define JWC_WPT_TILE_BOUNDS __launch_bounds__(512)
+#endif
+
 // Layout of this kernel's shared-memory lines: one pad slot per R double2, so a thread that
 // produces R outputs (window = R + L/2 - 1 consecutive double2 from a multiple of R) is R + 1 slots
 // away from its neighbour - an odd stride, conflict-free LDS.128 for R = 4 and R = 8.  A longer run
@@ -48,7 +56,7 @@ template <int R> __device__ __forceinline__ void lscalar_store(double2* buf, int
 // for every warp; JWC_WPT_TAIL_WARP selects who runs it: a dedicated extra warp (1) or one of the
 // main warps, rotating with the CTA and the level so that no SM sub-partition collects all of it (0).
 template <int L, int R, bool INPLACE>
-__global__ void __launch_bounds__(512)
+__global__ void JWC_WPT_TILE_BOUNDS
 k_wpt_fwd_tile(const __grid_constant__ Taps taps, const __grid_constant__ WptFwdArgs a) {
   extern __shared__ double2 smem2[];
   constexpr int lgR = (R == 8) ? 3 : 2;
@@ -60,6 +68,7 @@ k_wpt_fwd_tile(const __grid_constant__ Taps taps, const __grid_constant__ WptFwd
   const int base = tile * T;
   double2* cur = smem2;
   double2* nxt = INPLACE ? smem2 : smem2 + a.buf_cap;
+  first_wave_stagger(a.stagger_ns, a.stagger_ctas, a.stagger_div);
   {
     // stage the tile and its right halo; only the last tile of a line wraps (once: halo <= T / 4 < h).
     // nthr is a multiple of R, so a step of nthr double2 is a constant step through the padded layout.
@@ -325,6 +334,9 @@ static cudaError_t launch_LR(jwc_ctx* ctx, const Taps& taps, WptFwdArgs a, bool 
     if (inplace) smem /= 2;
     a.tiles_per_line = a.h / a.T;
     a.rot = (JWC_WPT_TAIL_WARP && ctx->rot_warps) ? 1 : 0;
+    a.stagger_ns = ctx->stagger;
+    a.stagger_div = ctx->sm_count;
+    a.stagger_ctas = ctx->sm_count * 8;
     a.lg_tpl = ilog2(a.tiles_per_line);
     a.lg_T = ilog2(a.T);
     grid = a.lines * a.tiles_per_line;
@@ -335,10 +347,12 @@ static cudaError_t launch_LR(jwc_ctx* ctx, const Taps& taps, WptFwdArgs a, bool 
   }
   if (grid > 0x7fffffff) return cudaErrorInvalidConfiguration;
   auto kern = resident ? k_wpt_fwd_res<L, R> : inplace ? k_wpt_fwd_tile<L, R, true> : k_wpt_fwd_tile<L, R, false>;
+  if (!resident) smem += size_t(ctx->xsmem) << 10;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
   }
+  if (ctx->carve) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   prof_begin(ctx, resident ? "k_wpt_fwd:resident" : "k_wpt_fwd:tile", double(a.lines) * a.h, a.m);
   kern<<<int(grid), nthr, smem, ctx->stream>>>(taps, a);
   prof_end(ctx);

@@ -22,6 +22,14 @@
 
 namespace jwc {
 
+// Launch bound of the tile kernels.  -DJWC_WPT_MINB=n builds them for 160-thread CTAs with n CTAs per SM (an A/B
+// switch for the register budget; the default keeps run-time CTA sizes up to 512).
+#ifdef JWC_WPT_MINB
+#define JWC_WPT_TILE_BOUNDS __launch_bounds__(160, JWC_WPT_MINB)
+#else
+#define JWC_WPT_TILE_BOUNDS __launch_bounds__(512)
+#endif
+
 // RS consecutive slots -> t[2 RS]; a2(w)/d2(w) = double2 (RS/2 g' + RS/2 - 1 - w); see jwc_fwt_rev.cu
 template <int L, int RS, class A2, class D2>
 __device__ __forceinline__ void wrev_step(const Taps& taps, A2 a2, D2 d2, double (&t)[2 * RS]) {
@@ -57,10 +65,20 @@ __device__ __forceinline__ void wrev_step(const Taps& taps, A2 a2, D2 d2, double
 // slots of left extension for the levels below (none at level 1).  The extension is a separate short
 // step, two slots per lane, run by a dedicated extra warp (JWC_WPT_TAIL_WARP = 1) or by one of the main
 // warps, rotating with the CTA and the level (0); see jwc_wpt_fwd.cu.
+//
+// Shared-memory layout of a node: double2 k at k + (k >> 3), one pad slot per 8 (rl).  The lanes of an LDS.128 phase
+// read windows 4 slots apart (8 g', ..): positions floor(9 (4 g' + c) / 8) hit the 8 bank groups 0,4,1,5,2,6,3,7; the
+// lanes of an STS.128 phase store runs of 8 slots, 9 positions apart: also 8 distinct groups.  Both are conflict-free
+// WITHOUT the rotated store order the stride-4 padding (pad2) needed - that cost 32 FSEL per level - and every 4-slot
+// block is contiguous, so a window is two block pointers plus compile-time offsets.
+__device__ __forceinline__ int rl(int k2) { return k2 + (k2 >> 3); }
+__host__ __device__ constexpr int rl_size(int n2) { return n2 + (n2 >> 3) + 2; }
+
 template <int L, int kRS, bool INPLACE>
-__global__ void __launch_bounds__(512)
+__global__ void JWC_WPT_TILE_BOUNDS
 k_wpt_rev_tile(const __grid_constant__ Taps taps, const __grid_constant__ WptRevArgs a) {
   extern __shared__ double2 smem2[];
+  __shared__ unsigned s_geo;
   constexpr int lgRS = (kRS == 8) ? 3 : 2;
   static_assert(kRS == 8 || kRS == 4, "kRS is 4 or 8");
   const int tid = rotated_tid(a.rot), nthr = blockDim.x, nmain = nthr - 32 * JWC_WPT_TAIL_WARP;
@@ -70,120 +88,117 @@ k_wpt_rev_tile(const __grid_constant__ Taps taps, const __grid_constant__ WptRev
   const int t0 = tile * T;
   double2* cur = smem2;
   double2* nxt = INPLACE ? smem2 : smem2 + a.buf_cap;
+  first_wave_stagger(a.stagger_ns, a.stagger_ctas, a.stagger_div);
   {
-    // stage all 2^m leaf packets: local sample i of node j is slot O + i (periodic) of packet j
+    // stage all 2^m leaf packets: local sample i of node j is slot O + i (periodic) of packet j.
+    // Thread j2 copies double2 number j2 of EVERY packet: the periodic source offset and the padded slot are the
+    // same for all of them, so the inner loop is one LDGSTS and two pointer increments (the flat loop over
+    // (packet, j2) items cost 40 instructions per item - half of this kernel's non-DFMA instructions).
     const int wm = h0 >> m;
-    const int O = (t0 >> m) - a.F[m] - a.ru8;
-    const int per_node = a.len[m] / 2;
+    const int O = (t0 >> m) - a.stage_left;
+    const int per_node = a.stage_len2, capm = a.cap_m, nn = 1 << m;
     const double* src = a.src + line * a.src_os;
-    const int total = per_node << m;
-    int node = 0;
-    for (int it = tid, j2 = tid; it < total; it += nthr, j2 += nthr) {
-      while (j2 >= per_node) { j2 -= per_node; ++node; }
-      cp_async16(&cur[node * a.cap[m] + pad2(j2)], src + node * wm + ((O + 2 * j2) & (wm - 1)));
+    for (int j2 = tid; j2 < per_node; j2 += nthr) {
+      const double* sp = src + ((O + 2 * j2) & (wm - 1));
+      double2* dp = cur + rl(j2);
+#pragma unroll 4
+      for (int node = 0; node < nn; ++node, sp += wm, dp += capm) cp_async16(dp, sp);
     }
+    if (tid == 0) s_geo = a.geo;
     cp_async_wait_all();
     __syncthreads();
   }
-  // one group of kRS slots of parent `par`: t[2 kRS] from the children's windows in `cur`
-  auto main_step = [&](int k, int par, int g, double (&t)[2 * kRS]) {
-    const int cap_in = a.cap[k];
+  // one group of kRS slots of parent `par`: t[2 kRS] from the children's windows.  G = first 4-slot block of the
+  // group's window in the children (g0_k + group number, in units of 4 double2).
+  auto main_step = [&](const double2* A, int cap_in, int G, double (&t)[2 * kRS]) {
+    const double2* D = A + cap_in;
     if constexpr (kRS == 8) {
-      const double2* A = cur + (2 * par) * cap_in + 5 * (a.g0[k] + g);  // pad2(4g'+3-w) = 5g' + (3-w) + floor((3-w)/4)
-      const double2* D = A + cap_in;
-      wrev_step<L, 8>(taps, [&](int w) { return A[(3 - w) + ((3 - w) >> 2)]; },
-                      [&](int w) { return D[(3 - w) + ((3 - w) >> 2)]; }, t);
+      // slot 4G + 3 - w sits in 4-block G - (w >> 2).  Blocks G, G - 2, .. are 9 positions apart from o1 = rl(4G),
+      // blocks G - 1, G - 3, .. from o0 = rl(4 (G - 1)): two run-time offsets, everything else folds (block G - 1 is
+      // never read for L = 2, whose window is 4 slots).
+      const int o1 = 4 * G + (G >> 1), o0 = 4 * (G - 1) + ((G - 1) >> 1);
+      auto at = [&](const double2* X, int w) {
+        const int blk = w >> 2, e = 3 - (w & 3) - 9 * (blk >> 1);
+        return (blk & 1) ? X[o0 + e] : X[o1 + e];
+      };
+      wrev_step<L, 8>(taps, [&](int w) { return at(A, w); }, [&](int w) { return at(D, w); }, t);
     } else {
-      const double2* A = cur + (2 * par) * cap_in;
-      const double2* D = A + cap_in;
-      const int c = 4 * a.g0[k] + (kRS / 2) * g + kRS / 2 - 1;
-      wrev_step<L, kRS>(taps, [&](int w) { return A[pad2(c - w)]; }, [&](int w) { return D[pad2(c - w)]; }, t);
+      // slots 2G' + 1 - w with G' = 2 g0 + group number (units of 2 double2): blocks of 2 never straddle a pad
+      wrev_step<L, kRS>(taps, [&](int w) { return A[rl(2 * G + 1 - w)]; }, [&](int w) { return D[rl(2 * G + 1 - w)]; }, t);
     }
   };
-  auto main_store = [&](int k, int par, int g, int gl, const double (&t)[2 * kRS]) {
+  auto main_store = [&](int k, double2* Yn, int g, int gl, const double (&t)[2 * kRS]) {
     if (k > 1) {
-      // pad2(kRS g + e) == kRS g + (kRS / 4) g + e + (e >> 2)
-      double2* Y = nxt + par * a.cap[k - 1] + (kRS + kRS / 4) * g;
-      if constexpr (kRS == 8) {
-        // the lanes of an STS.128 phase are 10 slots apart - groups g and g + 4 share a bank group.
-        // Lanes with bit 2 of g set store their upper four slots first: slot e ^ 4 sits 5 padded
-        // slots from slot e, an odd distance, which separates the two halves of the phase.
-        const bool rot = (g >> 2) & 1;
-        double2* Ylo = Y + (rot ? 5 : 0);
-        double2* Yhi = Y - (rot ? 5 : 0);
+      double2* Y = Yn + rl(kRS * g);  // kRS = 8: 9 g; kRS = 4: runs of 4 inside one 8-block
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-          Ylo[e] = make_double2(rot ? t[2 * e + 8] : t[2 * e], rot ? t[2 * e + 9] : t[2 * e + 1]);
-#pragma unroll
-        for (int e = 4; e < 8; ++e)
-          Yhi[e + 1] = make_double2(rot ? t[2 * e - 8] : t[2 * e], rot ? t[2 * e - 7] : t[2 * e + 1]);
-      } else {
-#pragma unroll
-        for (int e = 0; e < kRS; ++e) Y[e + (e >> 2)] = make_double2(t[2 * e], t[2 * e + 1]);
-      }
+      for (int e = 0; e < kRS; ++e) Y[e] = make_double2(t[2 * e], t[2 * e + 1]);
     } else {
       double* y = a.dst + line * a.dst_os + t0 + 2 * kRS * (g - gl);
 #pragma unroll
       for (int e = 0; e < kRS / 2; ++e) st_global_v4(y + 4 * e, t[4 * e], t[4 * e + 1], t[4 * e + 2], t[4 * e + 3]);
     }
   };
-  // two slots of left extension (tail step number g of parent `par`)
-  auto tail_step = [&](int k, int par, int g, double (&t)[4]) {
-    const double2* A = cur + (2 * par) * a.cap[k];
-    const double2* D = A + a.cap[k];
-    const int c = 4 * a.g0[k] + g;
-    wrev_step<L, 2>(taps, [&](int w) { return A[pad2(c - w)]; }, [&](int w) { return D[pad2(c - w)]; }, t);
+  // two slots of left extension (tail step number g of a parent): slots 4 g0 + g - w of the children
+  auto tail_step = [&](const double2* A, int cap_in, int c, double (&t)[4]) {
+    const double2* D = A + cap_in;
+    wrev_step<L, 2>(taps, [&](int w) { return A[rl(c - w)]; }, [&](int w) { return D[rl(c - w)]; }, t);
   };
-  auto tail_store = [&](int k, int par, int g, const double (&t)[4]) {
-    double2* Y = nxt + par * a.cap[k - 1];
-    Y[pad2(2 * g)] = make_double2(t[0], t[1]);
-    Y[pad2(2 * g + 1)] = make_double2(t[2], t[3]);
+  auto tail_store = [&](double2* Yn, int g, const double* t) {
+    Yn[rl(2 * g)] = make_double2(t[0], t[1]);
+    Yn[rl(2 * g + 1)] = make_double2(t[2], t[3]);
   };
 
   if constexpr (INPLACE) {
     // One item per thread and level (the launcher checks it): results wait in registers until every
     // window of the level has been read, then overwrite the level's input - one buffer instead of two,
     // more CTAs per SM, one more barrier per level (see jwc_wpt_fwd.cu).
+    // The per-level geometry is UNPACKED from one register (a.geo, read back from shared memory so that ptxas keeps
+    // it in a register) instead of being read from arrays indexed by the loop counter: every such read is an LDC,
+    // ptxas re-issues them in every level rather than hold registers, and constant loads into vector registers share
+    // the LSU data pipe with the window loads (profiles/r02_lsu_bound.md).  Geometry (launcher): every level k >= 2
+    // computes the same Fx slots of left extension, node capacities are capB >> k.
+    const unsigned geo = s_geo;
+    const int capB = geo & 0xffff, Fx = (geo >> 16) & 63, ru8 = (geo >> 22) & 31, lgT = geo >> 27;
     for (int k = m; k >= 1; --k) {
       double t[2 * kRS];
       int par = 0, g = 0;
       bool has = false;
-      const int gl = a.F[k] >> lgRS;
+      const int Fk = k == 1 ? 0 : Fx;                          // F_1 == 0: no extension at the output level
+      const int cap_in = capB >> k, cap_out = capB >> (k - 1);
+      const int g0k = k == m ? (ru8 >> 3) : ((2 * Fx - Fk) >> 3);
+      const int gl = Fk >> lgRS;
       if (tid < nmain) {
-        const int lg_gpp = a.lg_T - k - lgRS;
+        const int lg_gpp = lgT - k - lgRS;
         par = tid >> lg_gpp;
         g = gl + (tid & ((1 << lg_gpp) - 1));
-        main_step(k, par, g, t);
+        main_step(cur + (2 * par) * cap_in, cap_in, (kRS == 8 ? g0k : 2 * g0k) + g, t);
       } else if (k > 1) {
-        const int per_par = a.F[k] >> 1;
+        const int per_par = Fk >> 1;
         g = tid - nmain;
         has = g < (per_par << (k - 1));
         if (has) {
           while (g >= per_par) { g -= per_par; ++par; }
           double t4[4];
-          tail_step(k, par, g, t4);
+          tail_step(cur + (2 * par) * cap_in, cap_in, 4 * g0k + g, t4);
           t[0] = t4[0]; t[1] = t4[1]; t[2] = t4[2]; t[3] = t4[3];
         }
       }
       if (k > 1) __syncthreads();
-      if (tid < nmain) {
-        main_store(k, par, g, gl, t);
-      } else if (has) {
-        const double t4[4] = {t[0], t[1], t[2], t[3]};
-        tail_store(k, par, g, t4);
-      }
+      if (tid < nmain) main_store(k, nxt + par * cap_out, g, gl, t);
+      else if (has) tail_store(nxt + par * cap_out, g, t);
       if (k > 1) __syncthreads();
     }
   } else {
     for (int k = m; k >= 1; --k) {
+      const int cap_in = a.cap[k], cap_out = a.cap[k - 1], g0k = a.g0[k];
       if (tid < nmain) {
         const int lg_gpp = a.lg_T - k - lgRS;  // kept groups per parent = (T >> k) / kRS
         const int gl = a.F[k] >> lgRS;         // groups of left extension in front of them
         for (int it = tid; it < ((T >> 1) >> lgRS); it += nmain) {
           const int par = it >> lg_gpp, g = gl + (it & ((1 << lg_gpp) - 1));
           double t[2 * kRS];
-          main_step(k, par, g, t);
-          main_store(k, par, g, gl, t);
+          main_step(cur + (2 * par) * cap_in, cap_in, (kRS == 8 ? g0k : 2 * g0k) + g, t);
+          main_store(k, nxt + par * cap_out, g, gl, t);
         }
       }
       const int tail_warp = JWC_WPT_TAIL_WARP ? (nmain >> 5) : int((blockIdx.x + k) % unsigned(nthr >> 5));
@@ -194,8 +209,8 @@ k_wpt_rev_tile(const __grid_constant__ Taps taps, const __grid_constant__ WptRev
         for (int it = tid & 31, g = it; it < items; it += 32, g += 32) {
           while (g >= per_par) { g -= per_par; ++par; }
           double t[4];
-          tail_step(k, par, g, t);
-          tail_store(k, par, g, t);
+          tail_step(cur + (2 * par) * cap_in, cap_in, 4 * g0k + g, t);
+          tail_store(nxt + par * cap_out, g, t);
         }
       }
       __syncthreads();
@@ -294,25 +309,33 @@ k_wpt_rev_res(const __grid_constant__ Taps taps, const __grid_constant__ WptRevA
 static int round_up8(int v) { return (v + 7) & ~7; }
 
 // Fills the per-level geometry of a tile-mode launch and returns its shared memory (bytes).
+// Level k computes, besides the T >> k slots the tile keeps, F_k slots of left extension for the levels below:
+// F_1 = 0 and F_k = Fx = round_up8(L / 2) for every k >= 2 - the fixed point of F = round_up8((F + L/2) / 2), i.e.
+// enough at every depth (level 2 alone would get by with round_up8(L / 4)) - and a node of level k owns capB >> k
+// double2 of a buffer.  One F and one capacity base: the kernel derives the whole geometry from the packed word
+// a.geo instead of per-level tables.
 static size_t wpt_rev_tile_geometry(int L, WptRevArgs& a) {
   a.ru8 = round_up8(L / 2 - 1);
-  int N = 0;
-  for (int k = 1; k <= a.m; ++k) {
-    a.F[k] = round_up8((N + 1) / 2);
-    N = a.F[k] + L / 2 - 1;
-  }
+  const int Fx = round_up8(L / 2);
+  a.F[1] = 0;
+  for (int k = 2; k <= a.m; ++k) a.F[k] = Fx;
   a.F[a.m + 1] = 0;
-  int cap = 0;
+  int capB = 0;
   for (int k = 1; k <= a.m; ++k) {
     a.len[k] = (k == a.m) ? (a.T >> k) + a.F[k] + a.ru8 : (a.T >> k) + 2 * a.F[k + 1];
     a.g0[k] = (k == a.m) ? a.ru8 / 8 : (2 * a.F[k + 1] - a.F[k]) / 8;
-    a.cap[k] = pad2_size(a.len[k] / 2);
-    const int c = (1 << k) * a.cap[k];
-    if (c > cap) cap = c;
+    const int c = rl_size(a.len[k] / 2) << k;
+    if (c > capB) capB = c;
   }
+  capB = (capB + (1 << a.m) - 1) & ~((1 << a.m) - 1);
+  for (int k = 1; k <= a.m; ++k) a.cap[k] = capB >> k;
   a.cap[0] = 0;
-  a.buf_cap = cap;
-  return size_t(2) * cap * sizeof(double2);
+  a.buf_cap = capB;
+  int lgT = 0;
+  while ((1 << lgT) < a.T) ++lgT;
+  a.geo = unsigned(capB) | unsigned(Fx) << 16 | unsigned(a.ru8) << 22 | unsigned(lgT) << 27;
+  a.geo_ok = capB < (1 << 16) && Fx < 64 && a.ru8 < 32;
+  return size_t(2) * capB * sizeof(double2);
 }
 
 int wpt_rev_tile_levels(int L, int T, int want, size_t smem_limit) {
@@ -337,12 +360,18 @@ static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, WptRevArgs a, bool r
         ctx->wpt_threads % 32)
       return cudaErrorInvalidValue;
     smem = wpt_rev_tile_geometry(L, a);
-    inplace = JWC_WPT_TAIL_WARP && ctx->wpt_inplace && ctx->wpt_threads - 32 == (a.T / 2) / (ctx->wpt_rs == 4 ? 4 : 8);
+    inplace = JWC_WPT_TAIL_WARP && ctx->wpt_inplace && a.geo_ok && ctx->wpt_threads - 32 == (a.T / 2) / (ctx->wpt_rs == 4 ? 4 : 8);
+    a.stage_left = a.F[a.m] + a.ru8;
+    a.stage_len2 = a.len[a.m] / 2;
+    a.cap_m = a.cap[a.m];
     for (int k = 2; k <= a.m; ++k)  // tail steps of a level: one per lane of the tail warp
       if (((a.F[k] >> 1) << (k - 1)) > 32) inplace = false;
     if (inplace) smem /= 2;
     a.tiles_per_line = a.h0 / a.T;
     a.rot = (JWC_WPT_TAIL_WARP && ctx->rot_warps) ? 1 : 0;
+    a.stagger_ns = ctx->stagger;
+    a.stagger_div = ctx->sm_count;
+    a.stagger_ctas = ctx->sm_count * 8;
     auto ilog2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
     a.lg_tpl = ilog2(a.tiles_per_line);
     a.lg_T = ilog2(a.T);
@@ -356,10 +385,12 @@ static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, WptRevArgs a, bool r
   auto kern = resident ? (ctx->wpt_rs == 4 ? k_wpt_rev_res<L, 4> : k_wpt_rev_res<L, 8>)
                        : inplace ? (ctx->wpt_rs == 4 ? k_wpt_rev_tile<L, 4, true> : k_wpt_rev_tile<L, 8, true>)
                                  : (ctx->wpt_rs == 4 ? k_wpt_rev_tile<L, 4, false> : k_wpt_rev_tile<L, 8, false>);
+  if (!resident) smem += size_t(ctx->xsmem) << 10;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
   }
+  if (ctx->carve) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   prof_begin(ctx, resident ? "k_wpt_rev:resident" : "k_wpt_rev:tile", double(a.lines) * a.h0, a.m);
   kern<<<int(grid), ctx->wpt_threads, smem, ctx->stream>>>(taps, a);
   prof_end(ctx);

@@ -393,3 +393,33 @@ def test_staging_pipeline_chunks():
     assert np.array_equal(one, many)
     close(one, co.batch_1d(co.FWT, co.FORWARD, "Daubechies4", x, 8), np.abs(x).max())
     ctx.close()
+
+
+def _tuned_context(monkeypatch, tune):
+    """A context created under JWC_TUNE (jwc_create reads the launch-shape switches once)."""
+    if tune:
+        monkeypatch.setenv("JWC_TUNE", tune)
+    else:
+        monkeypatch.delenv("JWC_TUNE", raising=False)
+    return jw.CudaContext(0)
+
+
+@pytest.mark.parametrize("cls", ["Haar1", "Legendre1", "Haar1Orthogonal"])
+def test_two_tap_shuffle_kernel(monkeypatch, cls):
+    """k_fwt_fwd_shfl2 (jwc_shfl.cu): forward FWT of the 2-tap filters in registers and warp shuffles, every level
+    count from 1 to full depth on widths that are and are not multiples of 256, against the oracle AND bit for bit
+    against the shared-memory tile kernels (JWC_TUNE shfl=0) - both evaluate fma(x1, h1, x0 * h0)."""
+    w = jw.WaveletBuilder.create(cls)
+    on = jw.CudaFastWaveletTransform(w, context=_tuned_context(monkeypatch, ""))
+    off = jw.CudaFastWaveletTransform(w, context=_tuned_context(monkeypatch, "shfl=0"))
+    for n, batch in ((256, 7), (512, 5), (1024, 3), (1 << 16, 2), (128, 4)):
+        x = rng_signal(n, batch, n)
+        for level in sorted({1, 2, 3, 4, 7, 8, 9, n.bit_length() - 1}):
+            if level > n.bit_length() - 1:
+                continue
+            got = on.forwardBatch(x, level)
+            want = np.stack([co.transform_1d(co.FWT, co.FORWARD, cls, x[b], level) for b in range(batch)])
+            close(got, want, np.abs(x).max())
+            assert np.array_equal(got, off.forwardBatch(x, level)), (n, level)
+            back = np.stack([co.transform_1d(co.FWT, co.REVERSE, cls, want[b], level) for b in range(batch)])
+            close(on.reverseBatch(want, level), back, np.abs(want).max())
