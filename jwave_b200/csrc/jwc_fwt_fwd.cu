@@ -42,8 +42,8 @@ k_fwt_fwd(const __grid_constant__ Taps taps, const FwtFwdArgs a) {
 
   if constexpr (!RESIDENT) {
     // ---------------- tile mode ----------------
-    const int64_t line = blockIdx.x / a.tiles_per_line;
-    const int tile = int(blockIdx.x % a.tiles_per_line);
+    const int64_t line = blockIdx.x >> a.lg_tpl;  // tiles per line: a power of two
+    const int tile = int(blockIdx.x) & (a.tiles_per_line - 1);
     const int T = a.T, m = a.m, h = a.h;
     const int H0 = ((1 << m) - 1) * (L - 2);
     const int n0 = T + H0;                       // samples staged at level 0 (even)
@@ -51,8 +51,22 @@ k_fwt_fwd(const __grid_constant__ Taps taps, const FwtFwdArgs a) {
     double2* nxt = smem2 + a.cap0;               // level k approximations
     const double* src = a.src + line * a.src_os;
     const int base = tile * T;
-    for (int k2 = tid; k2 < n0 / 2; k2 += nthr)
-      cp_async16(&cur[fl<L>(k2)], src + ((base + 2 * k2) & (h - 1)));   // periodic wrap of the halo
+    if constexpr (L <= kXorMaxL) {
+      for (int k2 = tid; k2 < n0 / 2; k2 += nthr)
+        cp_async16(&cur[fl<L>(k2)], src + ((base + 2 * k2) & (h - 1)));   // periodic wrap of the halo
+    } else {
+      // Long filters are bound by instruction issue: running pointers instead of a mask, a 64-bit multiply-add and
+      // a layout call per element (25 instructions each before).  Only the last tile of a line wraps, once
+      // (halo <= T / 8 < h); nthr is a multiple of 4, so a step of nthr double2 is nthr + nthr / 4 padded slots.
+      const int n2 = n0 >> 1, fit2 = min(n2, (h - base) >> 1), step = nthr + (nthr >> 2);
+      const double* sp = src + base + 2 * tid;
+      double2* dp = cur + pad2(tid);
+      int k2 = tid;
+      for (; k2 < fit2; k2 += nthr, sp += 2 * nthr, dp += step) cp_async16(dp, sp);
+      sp -= h;
+#pragma unroll 1
+      for (; k2 < n2; k2 += nthr, sp += 2 * nthr, dp += step) cp_async16(dp, sp);
+    }
     cp_async_wait_all();
     __syncthreads();
 
@@ -181,6 +195,9 @@ static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, FwtFwdArgs a, bool r
     a.cap1 = fl_size<L>(((a.T >> 1) + H1) / 2 + 4);
     smem = size_t(a.cap0 + a.cap1) * sizeof(double2);
     a.tiles_per_line = a.h / a.T;
+    a.lg_tpl = 0;
+    while ((1 << a.lg_tpl) < a.tiles_per_line) ++a.lg_tpl;
+    if ((1 << a.lg_tpl) != a.tiles_per_line || ctx->fwd_threads % 4) return cudaErrorInvalidValue;
     const int64_t ctas = a.lines * a.tiles_per_line;
     if (ctas > 0x7fffffff) return cudaErrorInvalidConfiguration;
     grid = int(ctas);

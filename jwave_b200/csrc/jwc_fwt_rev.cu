@@ -104,8 +104,8 @@ k_fwt_rev(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevArgs 
 
   if constexpr (!RESIDENT) {
     // ---------------- tile mode ----------------
-    const int64_t line = blockIdx.x / a.tiles_per_line;
-    const int tile = int(blockIdx.x % a.tiles_per_line);
+    const int64_t line = blockIdx.x >> a.lg_tpl;  // tiles per line: a power of two
+    const int tile = int(blockIdx.x) & (a.tiles_per_line - 1);
     const int T = a.T;
     const int t0 = tile * T;
     const double* lineD = a.srcD + line * a.srcD_os;
@@ -271,6 +271,9 @@ static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, FwtRevArgs a, bool r
     a.offA[1] = off + capA[0];
     smem = size_t(off + capA[0] + capA[1]) * sizeof(double2);
     a.tiles_per_line = a.h0 / a.T;
+    a.lg_tpl = 0;
+    while ((1 << a.lg_tpl) < a.tiles_per_line) ++a.lg_tpl;
+    if ((1 << a.lg_tpl) != a.tiles_per_line) return cudaErrorInvalidValue;
     const int64_t ctas = a.lines * a.tiles_per_line;
     if (ctas > 0x7fffffff) return cudaErrorInvalidConfiguration;
     grid = int(ctas);

@@ -21,7 +21,7 @@ struct FwtFwdArgs {
   int m;                                // levels fused in this launch
   int T;                                // tile length (tile mode)
   int G;                                // lines per CTA (resident mode)
-  int tiles_per_line, cap0, cap1, tail; // filled in by the launcher
+  int tiles_per_line, lg_tpl, cap0, cap1, tail; // filled in by the launcher
   int rot;                              // rotate the warps' roles with the CTA number (rotated_tid)
 };
 // Longest filter whose FWT tile kernels get a tail warp: with both steps in one kernel body ptxas hoists
@@ -42,7 +42,7 @@ struct FwtRevArgs {
   int h0, m, T, G;
   RemoteMap rm;                         // mode 2: the output lines go to peer slabs
   // filled in by the launcher
-  int tiles_per_line, ru8, tail, rot;
+  int tiles_per_line, lg_tpl, ru8, tail, rot;
   int F[kMaxFuse + 2], g0[kMaxFuse + 1], len[kMaxFuse + 1], offD[kMaxFuse + 1], offA[2];
   int capC, capP[2];
 };
