@@ -130,6 +130,7 @@ struct jwc_ctx {
   int fwd_tile = 2048, fwd_m = 4 /* cap on the halo rule */, fwd_r = 4, rev_tile = 4096, rev_m = 3, rev_rs = 4, fwd_threads = 128, rev_threads = 128, res_cap = 256, res_threads = 128, wpt_tile = 2048, wpt_m = 3, wpt_threads = 160, wpt_rs = 8, wpt_r = 8, wpt_inplace = 1, rev_tail = 1, fwd_tail = 1;
   int str_tile = 512, str_rev_tile = 512, str_rev_m = 5, str_cap = 512, str_threads = 128, str_rev_threads = 128, str_tma = 1;  // strided-axis kernels
   // second-generation strided kernels (inner % 16 == 0): on/off, tile rows, resident cap, forced levels per pass (0 = halo rule)
+  int wpt_transpose = 1;  // WPT along strided axes: transpose -> fused contiguous plan -> transpose (0: one-level kernels)
   int res_kb = 48;    // resident kernels: shared-memory budget per CTA (KB) that sets the lines per CTA
   int stagger = 0;    // WPT tile kernels: first-wave stagger in ns per resident-CTA slot (jwc_fused.cuh)
   int xsmem = 0;      // extra dynamic shared memory (KB) per CTA of the WPT tile kernels: an A/B knob that LOWERS the CTAs per SM

@@ -11,6 +11,9 @@ namespace jwc {
 #endif
 
 
+// ---- batched transpose [batch][R][C] -> [batch][C][R] (jwc_transpose.cu) ------------------------
+cudaError_t launch_transpose(jwc_ctx* ctx, const double* in, double* out, int64_t batch, int R, int C);
+
 // ---- forward FWT, contiguous lines (jwc_fwt_fwd.cu) -----------------------------------------
 struct FwtFwdArgs {
   const double* src; int64_t src_os;    // input lines of width h (stride between lines, in doubles)

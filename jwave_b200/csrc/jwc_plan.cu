@@ -394,8 +394,31 @@ static cudaError_t wpt_reverse_generic(jwc_ctx* ctx, const WaveletRec& w, const 
 // `out` and one scratch buffer, phased so the last pass writes `out`.
 static const size_t kWptSmemLimit = 112 * 1024;  // two CTAs per SM
 
+// Packet transform along a STRIDED axis (inner > 1: matrix columns, the outer axes of a volume): transpose the
+// [n][inner] planes so that the axis becomes contiguous, run the fused contiguous-line plan, transpose back
+// (jwc_transpose.cu).  Buffers: `out` holds the transposed input, scratch[1] the transposed result; the fused plan
+// ping-pongs between scratch[1] and scratch[0] as usual.
+static bool wpt_transposed_ok(const jwc_ctx* ctx, bool mirror, const double* in, const double* out, int n, int64_t inner, int level) {
+  return mirror && !ctx->force_generic && ctx->wpt_transpose && inner > 1 && inner <= 0x7fffffff && n >= 8 && level >= 2 &&
+         aligned32(in) && aligned32(out);
+}
+static cudaError_t wpt_forward(jwc_ctx* ctx, const WaveletRec& w, const double* in, double* out,
+                               int64_t outer, int n, int64_t inner, int level);
+static cudaError_t wpt_reverse(jwc_ctx* ctx, const WaveletRec& w, const double* in, double* out,
+                               int64_t outer, int n, int64_t inner, int level);
+static cudaError_t wpt_transposed(jwc_ctx* ctx, const WaveletRec& w, int dir, const double* in, double* out,
+                                  int64_t outer, int n, int64_t inner, int level) {
+  double* X = nullptr;
+  JWC_TRY(ensure_scratch(ctx, 1, size_t(outer) * n * inner * sizeof(double), &X));
+  JWC_TRY(launch_transpose(ctx, in, out, outer, n, int(inner)));
+  if (dir == JWC_FORWARD) JWC_TRY(wpt_forward(ctx, w, out, X, outer * inner, n, 1, level));
+  else JWC_TRY(wpt_reverse(ctx, w, out, X, outer * inner, n, 1, level));
+  return launch_transpose(ctx, X, out, outer, int(inner), n);
+}
+
 static cudaError_t wpt_forward(jwc_ctx* ctx, const WaveletRec& w, const double* in, double* out,
                                int64_t outer, int n, int64_t inner, int level) {
+  if (wpt_transposed_ok(ctx, w.mirror_de, in, out, n, inner, level)) return wpt_transposed(ctx, w, JWC_FORWARD, in, out, outer, n, inner, level);
   if (!w.mirror_de || !fused_ok(ctx, in, out, n, inner) || n < 8) return wpt_forward_generic(ctx, w, in, out, outer, n, inner, level);
   struct Pass { int h, m; bool resident; };
   Pass passes[32];
@@ -428,6 +451,7 @@ static cudaError_t wpt_forward(jwc_ctx* ctx, const WaveletRec& w, const double* 
 
 static cudaError_t wpt_reverse(jwc_ctx* ctx, const WaveletRec& w, const double* in, double* out,
                                int64_t outer, int n, int64_t inner, int level) {
+  if (wpt_transposed_ok(ctx, w.mirror_re, in, out, n, inner, level)) return wpt_transposed(ctx, w, JWC_REVERSE, in, out, outer, n, inner, level);
   if (!w.mirror_re || !fused_ok(ctx, in, out, n, inner) || n < 8) return wpt_reverse_generic(ctx, w, in, out, outer, n, inner, level);
   // Output widths of the passes, chosen backwards from n: each tile pass rebuilds as many levels
   // as its shared memory allows; whatever is left below res_cap is one resident pass.

@@ -3,7 +3,8 @@
 //
 //   tools/qbench <workload> <steps> [tune ...]          (tune = a JWC_TUNE string, "" = defaults)
 //     workloads: c2 c3 c4 c5 (BASELINE.json's configs; c4 on QB_BATCH images, default 4), h1 (Haar1 FWT, c2's shape),
-//                d10 / d20 / s20 (Daubechies10 / 20, Symlet20 FWT on c2's shape), w20 (Daubechies20 WPT, c3's shape)
+//                d10 / d20 / s20 (Daubechies10 / 20, Symlet20 FWT on c2's shape), w20 (Daubechies20 WPT, c3's shape),
+//                w2d / w3d (Symlet8 WPT on 4 x 4096^2 images, 6 levels per axis / on a 512^3 volume, 5 levels)
 //   QB_KERNELS=1 adds the per-kernel table of jwc_profile_report to every variant.
 //
 // Every variant runs on its own context (jwc_create reads JWC_TUNE): `steps` forward + reverse passes timed with CUDA
@@ -62,6 +63,8 @@ static int run(jwc_ctx* c, int wid, const Work& w, int dir, const double* in, do
     case 0: return jwc_fwt1d_dev(c, wid, dir, in, out, w.batch, w.n, w.level);
     case 1: return jwc_wpt1d_dev(c, wid, dir, in, out, w.batch, w.n, w.level);
     case 2: return jwc_fwt2d_dev(c, wid, dir, in, out, w.batch, w.n, w.n, w.level, w.level);
+    case 4: return jwc_wpt2d_dev(c, wid, dir, in, out, w.batch, w.n, w.n, w.level, w.level);
+    case 5: return jwc_wpt3d_dev(c, wid, dir, in, out, w.n, w.n, w.n, w.level, w.level, w.level);
     default: return jwc_fwt3d_dev(c, wid, dir, in, out, w.n, w.n, w.n, w.level, w.level, w.level);
   }
 }
@@ -81,14 +84,16 @@ int main(int argc, char** argv) {
   else if (wl == "w20") w = {"Daubechies20", 1, 1 << 16, 6, 4096};
   else if (wl == "c4") w = {"Daubechies20", 2, 8192, 13, 4};
   else if (wl == "c5") w = {"Coiflet5", 3, 1024, 10, 1};
+  else if (wl == "w2d") w = {"Symlet8", 4, 4096, 6, 4};
+  else if (wl == "w3d") w = {"Symlet8", 5, 512, 5, 1};
   else { printf("unknown workload %s\n", wl.c_str()); return 1; }
   if (qb > 0) w.batch = qb;
   const QTaps* tp = nullptr;
   for (const QTaps& t : kQTaps) if (!strcmp(t.name, w.wavelet)) tp = &t;
   if (!tp) { printf("no taps for %s\n", w.wavelet); return 1; }
   size_t count = size_t(w.batch) * w.n;
-  if (w.kind == 2) count *= w.n;
-  if (w.kind == 3) count = size_t(w.n) * w.n * w.n;
+  if (w.kind == 2 || w.kind == 4) count *= w.n;
+  if (w.kind == 3 || w.kind == 5) count = size_t(w.n) * w.n * w.n;
   double *x, *y, *z, *ref, *d_tmp;
   CK(cudaMalloc(&x, count * 8)); CK(cudaMalloc(&y, count * 8)); CK(cudaMalloc(&z, count * 8)); CK(cudaMalloc(&ref, count * 8));
   CK(cudaMalloc(&d_tmp, 8));
@@ -97,12 +102,13 @@ int main(int argc, char** argv) {
   // flops per sample (direct form), as bench.py counts them
   const int L = tp->L;
   double flops;
-  if (w.kind == 1) flops = 2.0 * L * w.level;
+  const int axes = (w.kind == 0 || w.kind == 1) ? 1 : (w.kind == 2 || w.kind == 4) ? 2 : 3;
+  if (w.kind == 1 || w.kind >= 4) flops = 2.0 * L * w.level * axes;
   else {
     const double per_axis = 4.0 * L * (1.0 - 1.0 / double(1 << w.level));
-    flops = per_axis * (w.kind == 0 ? 1 : w.kind == 2 ? 2 : 3);
+    flops = per_axis * axes;
   }
-  const double t_hbm = 16.0 * (w.kind == 0 || w.kind == 1 ? 1 : w.kind == 2 ? 2 : 3) / 6454.6e9, t_fp = flops / 36.7e12;
+  const double t_hbm = 16.0 * axes / 6454.6e9, t_fp = flops / 36.7e12;
   const double t_roof = t_hbm > t_fp ? t_hbm : t_fp;
   printf("# %s: %s kind %d n %d level %d batch %lld  (%.3f G samples, roofline %s)\n", wl.c_str(), w.wavelet, w.kind, w.n, w.level,
          (long long)w.batch, count / 1e9, t_hbm > t_fp ? "hbm" : "fp64");
