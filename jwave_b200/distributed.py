@@ -146,8 +146,10 @@ class PeerSlabVolumeTransform:
             self._peer = getattr(self, "_peer", {})
             self._peer[key] = [h.get_buffer(r, (numel,), torch.float64) for r in range(W)]
             self._ptrs[key] = [t_.data_ptr() for t_ in self._peer[key]]
-        # "copies": chunks per re-cut (JWB_SLAB_CHUNKS overrides); each chunk keeps whole 16-column blocks
-        C = int(os.environ.get("JWB_SLAB_CHUNKS", chunks or 4))
+        # "copies": chunks per re-cut (JWB_SLAB_CHUNKS overrides); each chunk keeps whole 16-column blocks.  Measured
+        # on 1024^3 (gpurun_out -> profiles/r02_bench_c5_n*.json): 2 GPUs 84 / 92 / 88 GS/s with 2 / 4 / 8 chunks,
+        # 4 GPUs 177 / 175, 8 GPUs 297 / 263 / 225 - the slabs of 8 GPUs are 128 rows, finer chunks stop paying
+        C = int(os.environ.get("JWB_SLAB_CHUNKS", chunks or (2 if W >= 8 else 4)))
         while C > 1 and (self.p % C or self.q % C or (self.q // C) * R % 16):
             C //= 2
         self.chunks = max(C, 1)
