@@ -521,6 +521,16 @@ static int aed_dev(jwc_ctx* ctx, int wid, int kind, int dir, const double* in, d
     if (!((n >> p) & 1)) continue;
     const int len = 1 << p;
     const size_t row = size_t(len) * sizeof(double);
+    // FWT blocks of at least 4 samples in signals whose length is a multiple of 4: the fused kernels read and write
+    // the block in place of the signal (line pitch n), no gather / scatter passes (2 x 16 B per sample less)
+    if (kind == JWC_FWT && p >= 2 && jwc::fwt_pitched_ok(ctx, ctx->wavelets[wid], dir, in + off, out + off, len, n, n)) {
+      ctx->pitch_in = ctx->pitch_out = n;
+      st = axis_dev(ctx, wid, kind, dir, in + off, out + off, batch, len, 1, p);
+      ctx->pitch_in = ctx->pitch_out = 0;
+      if (st) return st;
+      off += len;
+      continue;
+    }
     JWC_CUDA(ctx, cudaMemcpy2DAsync(dense_in, row, in + off, pitch, row, size_t(batch), cudaMemcpyDeviceToDevice, ctx->stream));
     if ((st = axis_dev(ctx, wid, kind, dir, dense_in, dense_out, batch, len, 1, p))) return st;
     JWC_CUDA(ctx, cudaMemcpy2DAsync(out + off, pitch, dense_out, row, row, size_t(batch), cudaMemcpyDeviceToDevice, ctx->stream));

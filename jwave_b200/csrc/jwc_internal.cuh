@@ -119,6 +119,9 @@ struct jwc_ctx {
   std::string err;
   int64_t launches = 0;
   const jwc::RemoteMap* remote = nullptr;  // set for the duration of one jwc_axis_dev_remote call
+  // Line pitches (doubles) of `in` / `out` when the lines of a contiguous FWT are NOT dense (0 = dense): set by
+  // jwc_aed1d for the duration of one block transform, honoured by the fused contiguous FWT plans only (jwc_plan.cu)
+  int64_t pitch_in = 0, pitch_out = 0;
   bool prof_on = false;
   std::vector<jwc::ProfRec> prof;
   jwc::Scratch scratch[4];      // [0],[1]: level ping-pong; [2]: axis ping-pong; [3]: alias guard

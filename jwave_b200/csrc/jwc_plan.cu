@@ -230,9 +230,10 @@ static cudaError_t fwt_forward(jwc_ctx* ctx, const WaveletRec& w, const double* 
   double* S[2] = {nullptr, nullptr};
   for (int i = 0; i < 2; ++i)
     if (need[i]) JWC_TRY(ensure_scratch(ctx, i, need[i], &S[i]));
+  const int64_t pin = ctx->pitch_in ? ctx->pitch_in : n, pout = ctx->pitch_out ? ctx->pitch_out : n;
   FwtFwdArgs a;
-  a.src = in; a.src_os = n;
-  a.dstD = out; a.dstD_os = n;
+  a.src = in; a.src_os = pin;
+  a.dstD = out; a.dstD_os = pout;
   a.lines = outer;
   for (int i = 0; i < npass; ++i) {
     const Pass& p = passes[i];
@@ -240,7 +241,7 @@ static cudaError_t fwt_forward(jwc_ctx* ctx, const WaveletRec& w, const double* 
     a.h = p.h; a.T = p.T; a.m = p.m;
     a.G = p.resident ? resident_lines(ctx, p.h, 150) : 1;   // fwd: (h/2 + h/4) double2, padded 1.25
     a.dstA = last ? out : S[(i + 1) & 1];
-    a.dstA_os = last ? n : (p.h >> p.m);
+    a.dstA_os = last ? pout : (p.h >> p.m);
     cudaError_t e = p.shfl ? launch_fwt_fwd_shfl(ctx, w.L, w.de, a) : cudaErrorNotSupported;
     if (e == cudaErrorNotSupported) {
       if (p.shfl) {  // declined (alignment): the tile kernel takes the same pass if it can fuse that many levels
@@ -326,9 +327,10 @@ static cudaError_t fwt_reverse(jwc_ctx* ctx, const WaveletRec& w, const double* 
   double* S[2] = {nullptr, nullptr};
   for (int i = 0; i < 2; ++i)
     if (need[i]) JWC_TRY(ensure_scratch(ctx, i, need[i], &S[i]));
+  const int64_t pin = ctx->pitch_in ? ctx->pitch_in : n, pout = ctx->pitch_out ? ctx->pitch_out : n;
   FwtRevArgs a;
-  a.srcA = in; a.srcA_os = n;
-  a.srcD = in; a.srcD_os = n;
+  a.srcA = in; a.srcA_os = pin;
+  a.srcD = in; a.srcD_os = pin;
   a.lines = outer;
   for (int i = 0; i < npass; ++i) {
     const Pass& p = passes[i];
@@ -337,7 +339,7 @@ static cudaError_t fwt_reverse(jwc_ctx* ctx, const WaveletRec& w, const double* 
     a.T = (p.resident || p.h0 < ctx->rev_tile) ? p.h0 : ctx->rev_tile;
     a.G = p.resident ? resident_lines(ctx, p.h0, 140) : 1;  // rev: (h + h/2 + h/4) samples, unpadded
     a.dst = last ? out : S[i & 1];
-    a.dst_os = last ? n : p.h0;
+    a.dst_os = last ? pout : p.h0;
     a.rm = (last && ctx->remote) ? *ctx->remote : RemoteMap();
     JWC_TRY(launch_fwt_rev(ctx, w.L, w.re, a, p.resident));
     a.srcA = a.dst; a.srcA_os = a.dst_os;
@@ -494,6 +496,12 @@ static cudaError_t wpt_reverse(jwc_ctx* ctx, const WaveletRec& w, const double* 
     src = a.dst;
   }
   return cudaSuccess;
+}
+
+bool fwt_pitched_ok(const jwc_ctx* ctx, const WaveletRec& w, int dir, const double* in, const double* out, int n,
+                    int64_t pitch_in, int64_t pitch_out) {
+  return (dir == JWC_FORWARD ? w.mirror_de : w.mirror_re) && !ctx->remote && fused_ok(ctx, in, out, n, 1) &&
+         pitch_in % 4 == 0 && pitch_out % 4 == 0;
 }
 
 cudaError_t run_axis(jwc_ctx* ctx, const WaveletRec& w, int kind, int dir, const double* in, double* out,

@@ -10,6 +10,11 @@ namespace jwc {
 cudaError_t run_axis(jwc_ctx* ctx, const WaveletRec& w, int kind, int dir, const double* in, double* out,
                      int64_t outer, int n, int64_t inner, int level);
 
+// True if a contiguous FWT over lines of `n` samples that are pitch_in / pitch_out doubles apart (ctx->pitch_in,
+// ctx->pitch_out) takes the fused kernels, which honour the pitches; the one-level and strided plans assume dense lines.
+bool fwt_pitched_ok(const jwc_ctx* ctx, const WaveletRec& w, int dir, const double* in, const double* out, int n,
+                    int64_t pitch_in, int64_t pitch_out);
+
 cudaError_t ensure_scratch(jwc_ctx* ctx, int slot, size_t bytes, double** ptr);
 
 }  // namespace jwc

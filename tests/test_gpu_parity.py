@@ -249,10 +249,12 @@ def test_ancient_egyptian_decomposition(kind):
             cf = co.aed(okind(kind), co.FORWARD, cls, x)
             close(aed.forward(x), cf, np.abs(x).max())
             close(aed.reverse(cf), co.aed(okind(kind), co.REVERSE, cls, cf), np.abs(cf).max())
-        xb = rng_signal(5, 37, 1234)
-        cb = co.aed(okind(kind), co.FORWARD, cls, xb)
-        close(aed.forwardBatch(xb), cb, np.abs(xb).max())
-        close(aed.reverseBatch(cb), co.aed(okind(kind), co.REVERSE, cls, cb), np.abs(cb).max())
+        # 1234: gathered blocks; 1000 and 4100 (multiples of 4): FWT blocks run in place of the signals (line pitch n)
+        for width in (1234, 1000, 4100):
+            xb = rng_signal(5, 37, width)
+            cb = co.aed(okind(kind), co.FORWARD, cls, xb)
+            close(aed.forwardBatch(xb), cb, np.abs(xb).max())
+            close(aed.reverseBatch(cb), co.aed(okind(kind), co.REVERSE, cls, cb), np.abs(cb).max())
         assert jw.Transform(aed).forward(np.ones(12)) is not None
         with pytest.raises(jw.JWaveError):
             aed.forward(np.ones(12), 2)
