@@ -215,6 +215,13 @@ static cudaError_t fwt_forward(jwc_ctx* ctx, const WaveletRec& w, const double* 
       while (p.m < left && (h >> p.m) < 4) --p.m;
     } else if (p.resident) {
       p.m = left;
+      // deep tails: below ~32 samples per line a level keeps a fraction of the CTA's threads busy and still costs a
+      // barrier; with res_split the resident work is two launches - down to res_split samples, then the rest on
+      // (res_cap / res_split) times as many lines per CTA
+      if (ctx->res_split >= 4 && h > ctx->res_split && (h >> left) < ctx->res_split) {
+        p.m = 0;
+        while ((h >> p.m) > ctx->res_split) ++p.m;
+      }
     } else {
       int m_tile = fwt_tile_levels(w.L, p.T);
       if (ctx->fwd_m > 0 && ctx->fwd_m < m_tile) m_tile = ctx->fwd_m;
