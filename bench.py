@@ -568,7 +568,11 @@ def run_workload(name, args, env):
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from ncu --set full captures
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(f"{name}:{dom['kernel']}")
+        # per launch at the bench batch, or (c4 / c5: captured on a smaller batch) DRAM bytes per sample x samples per launch
+        tj = json.load(open(tpath))
+        traffic = tj.get(f"{name}:{dom['kernel']}")
+        if traffic is None and tj.get(f"{name}:{dom['kernel']}:per_sample") is not None:
+            traffic = tj[f"{name}:{dom['kernel']}:per_sample"] * dom["samples_per_launch"]
     t_hbm = samples * bytes_per_sample / (hbm_peak * 1e9)
     t_fp64 = samples * flops_per_sample / (FP64_PEAK_TFLOPS * 1e12)
     t_roof = max(t_hbm, t_fp64)
