@@ -135,7 +135,7 @@ class ClockSampler:
                     self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.005 if self._nvml is not None else 0.1)
+            self._stop.wait(float(os.environ.get("JWB_CLOCK_PERIOD", 0.005)) if self._nvml is not None else 0.1)
 
     def start(self):
         self._t.start()
