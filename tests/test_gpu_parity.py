@@ -149,6 +149,37 @@ def test_strided_axis_tile_and_resident(cls):
     dev.close()
 
 
+@pytest.mark.parametrize("cls", ["Haar1", "Daubechies4", "Symlet8", "Daubechies20"])
+def test_strided_axis_packet_transform_through_transposes(cls, monkeypatch):
+    """WPT along a strided axis = batched transpose -> fused contiguous plan -> transpose (jwc_transpose.cu,
+    jwc_plan.cu::wpt_transposed): any inner stride incl. ones that are not multiples of the 32-wide tile, partial and
+    full depth, against the oracle AND bit for bit against the one-level kernels (JWC_TUNE wpt_transpose=0)."""
+    import torch
+    from jwave_b200.device import DeviceTransforms
+    w = jw.WaveletBuilder.create(cls)
+    monkeypatch.delenv("JWC_TUNE", raising=False)
+    dev = DeviceTransforms(w)  # jwc_create reads JWC_TUNE once
+    monkeypatch.setenv("JWC_TUNE", "wpt_transpose=0")
+    plain = DeviceTransforms(w)
+    monkeypatch.delenv("JWC_TUNE")
+    for outer, n, inner, level in ((2, 256, 24, 5), (1, 64, 3, 6), (3, 32, 40, 2), (1, 1024, 17, 10), (2, 4096, 8, 6)):
+        x = rng_signal(n + inner, outer, n, inner)
+        def columns(direction, arr):
+            lines = np.ascontiguousarray(arr.transpose(0, 2, 1).reshape(-1, n))
+            res = co.batch_1d(co.WPT, direction, cls, lines, level)
+            return np.ascontiguousarray(res.reshape(outer, inner, n).transpose(0, 2, 1))
+        ref = columns(co.FORWARD, x)
+        xd = torch.from_numpy(x).cuda()
+        fd = dev.axis(_lib.WPT, _lib.FORWARD, xd, outer, n, inner, level)
+        close(fd.cpu().numpy(), ref, np.abs(x).max())
+        assert torch.equal(fd, plain.axis(_lib.WPT, _lib.FORWARD, xd, outer, n, inner, level))
+        back = columns(co.REVERSE, ref)
+        rd = dev.axis(_lib.WPT, _lib.REVERSE, torch.from_numpy(ref).cuda(), outer, n, inner, level)
+        close(rd.cpu().numpy(), back, np.abs(ref).max())
+    dev.close()
+    plain.close()
+
+
 @pytest.mark.parametrize("cls", ["Haar1", "Daubechies2", "Daubechies4", "Symlet8", "Coiflet5", "Daubechies20"])
 def test_strided_axis_second_generation_shapes(cls):
     """inner % 16 == 0 takes the 16-column kernels (jwc_fwt_strided2.cu): tile passes + resident tail, lines
