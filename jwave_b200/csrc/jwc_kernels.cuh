@@ -29,7 +29,10 @@ struct FwtFwdArgs {
 };
 // Longest filter whose FWT tile kernels get a tail warp: with both steps in one kernel body ptxas hoists
 // the taps of longer filters out of the level loop into vector registers (reverse L = 40: 66 -> 132).
-constexpr int kTailMaxL = 24;
+#ifndef JWC_TAIL_MAXL
+#define JWC_TAIL_MAXL 24
+#endif
+constexpr int kTailMaxL = JWC_TAIL_MAXL;
 int fwt_tile_levels(int L, int T);
 cudaError_t launch_fwt_fwd(jwc_ctx* ctx, int L, const Taps& taps, const FwtFwdArgs& a, bool resident);
 // jwc_shfl.cu: 2-tap filters, registers + warp shuffles, up to 8 levels per launch (cudaErrorNotSupported = declined)
