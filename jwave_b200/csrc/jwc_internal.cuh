@@ -134,6 +134,8 @@ struct jwc_ctx {
   int str_tile = 512, str_rev_tile = 512, str_rev_m = 5, str_cap = 512, str_threads = 128, str_rev_threads = 128, str_tma = 1;  // strided-axis kernels
   // second-generation strided kernels (inner % 16 == 0): on/off, tile rows, resident cap, forced levels per pass (0 = halo rule)
   int wpt_transpose = 1;  // WPT along strided axes: transpose -> fused contiguous plan -> transpose (0: one-level kernels)
+  int wpt_rev_m = 0;  // WPT reverse: levels per tile pass (0 = wpt_m); the reverse's left extension does not grow with depth
+  int wpt_tma_store = 1;  // WPT reverse tile kernel: finished tiles leave through cp.async.bulk.tensor stores
   int res_split = 0;  // resident FWT forward: split the resident work at this width (0 = one launch), jwc_plan.cu
   int res_kb = 48;    // resident kernels: shared-memory budget per CTA (KB) that sets the lines per CTA
   int stagger = 0;    // WPT tile kernels: first-wave stagger in ns per resident-CTA slot (jwc_fused.cuh)

@@ -115,6 +115,8 @@ struct WptRevArgs {
   int tiles_per_line, lg_tpl, lg_T, ru8, buf_cap, rot;
   int stagger_ns, stagger_ctas, stagger_div;  // first-wave stagger (A/B switch, jwc_fused.cuh)
   int stage_left, stage_len2, cap_m;    // tile mode, staging: F[m] + ru8, len[m] / 2, cap[m]
+  int stage_lg_lpn;                     // staging: log2 threads per packet when packets are short, else -1
+  int tma_out;                          // tile mode, in place: the finished tile leaves through a TMA store
   unsigned geo; int geo_ok;             // tile mode: capB | Fx << 16 | ru8 << 22 | lg T << 27 (jwc_wpt_rev.cu)
   int F[kMaxFuse + 2], g0[kMaxFuse + 1], len[kMaxFuse + 1], cap[kMaxFuse + 1];
 };

@@ -475,7 +475,8 @@ static cudaError_t wpt_reverse(jwc_ctx* ctx, const WaveletRec& w, const double* 
     if (wv <= ctx->res_cap) break;  // produced by the resident pass
     int want = 0;
     while ((cur0 << want) < wv) ++want;
-    if (want > ctx->wpt_m) want = ctx->wpt_m;
+    const int cap_m = ctx->wpt_rev_m > 0 ? ctx->wpt_rev_m : ctx->wpt_m;
+    if (want > cap_m) want = cap_m;
     wv >>= wpt_rev_tile_levels(w.L, wv < ctx->wpt_tile ? wv : ctx->wpt_tile, want, kWptSmemLimit);
   }
   for (int i = nw - 1, cur = cur0; i >= 0; --i) {

@@ -13,6 +13,10 @@
 //                                  N_k = F_k + L/2 - 1 coefficients left of the tile (see jwc_fwt_rev.cu).
 //   resident mode (h0 <= res_cap): G whole lines per CTA, wrap by index mask; nodes shorter than 8
 //                                  take a scalar path with true modular indexing.
+#include <cuda.h>
+
+#include <cstring>
+
 #include "jwc_fused.cuh"
 #include "jwc_kernels.cuh"
 
@@ -74,10 +78,21 @@ __device__ __forceinline__ void wrev_step(const Taps& taps, A2 a2, D2 d2, double
 __device__ __forceinline__ int rl(int k2) { return k2 + (k2 >> 3); }
 __host__ __device__ constexpr int rl_size(int n2) { return n2 + (n2 >> 3) + 2; }
 
+// TMA store of the finished tile (cp.async.bulk.tensor, SASS UTMASTG): box {16 doubles, T / 16 rows} of the output seen
+// as a [rows][16] matrix, read from a dense shared-memory image whose 16-byte chunks are XOR-swizzled by the row number
+// (SWIZZLE_128B) - the pattern that makes the threads' 128-byte row stores conflict-free.
+__device__ __forceinline__ void tma_store_tile(const void* tmap, const void* smem_src, int x, int y) {
+  const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_src));
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap), "r"(x), "r"(y), "r"(s)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the CTA's shared memory may go once it has been read
+}
+
 template <int L, int kRS, bool INPLACE>
 __global__ void JWC_WPT_TILE_BOUNDS
-k_wpt_rev_tile(const __grid_constant__ Taps taps, const __grid_constant__ WptRevArgs a) {
-  extern __shared__ double2 smem2[];
+k_wpt_rev_tile(const __grid_constant__ Taps taps, const __grid_constant__ WptRevArgs a, const __grid_constant__ CUtensorMap tmapOut) {
+  extern __shared__ __align__(1024) double2 smem2[];
   __shared__ unsigned s_geo;
   constexpr int lgRS = (kRS == 8) ? 3 : 2;
   static_assert(kRS == 8 || kRS == 4, "kRS is 4 or 8");
@@ -98,11 +113,26 @@ k_wpt_rev_tile(const __grid_constant__ Taps taps, const __grid_constant__ WptRev
     const int O = (t0 >> m) - a.stage_left;
     const int per_node = a.stage_len2, capm = a.cap_m, nn = 1 << m;
     const double* src = a.src + line * a.src_os;
-    for (int j2 = tid; j2 < per_node; j2 += nthr) {
-      const double* sp = src + ((O + 2 * j2) & (wm - 1));
-      double2* dp = cur + rl(j2);
+    if (a.stage_lg_lpn < 0) {
+      for (int j2 = tid; j2 < per_node; j2 += nthr) {
+        const double* sp = src + ((O + 2 * j2) & (wm - 1));
+        double2* dp = cur + rl(j2);
 #pragma unroll 4
-      for (int node = 0; node < nn; ++node, sp += wm, dp += capm) cp_async16(dp, sp);
+        for (int node = 0; node < nn; ++node, sp += wm, dp += capm) cp_async16(dp, sp);
+      }
+    } else {
+      // many short packets (a deep pass: 64 packets of 24 double2 at m = 6): 2^lg_lpn threads per packet, several
+      // packets per round
+      const int lpn = 1 << a.stage_lg_lpn, npi = nthr >> a.stage_lg_lpn;
+      const int j2 = tid & (lpn - 1), n0 = tid >> a.stage_lg_lpn;
+      if (j2 < per_node && n0 < npi) {
+        const double* sp = src + int64_t(n0) * wm + ((O + 2 * j2) & (wm - 1));
+        double2* dp = cur + n0 * capm + rl(j2);
+        const int64_t ss = int64_t(npi) * wm;
+        const int ds = npi * capm;
+#pragma unroll 4
+        for (int node = n0; node < nn; node += npi, sp += ss, dp += ds) cp_async16(dp, sp);
+      }
     }
     if (tid == 0) s_geo = a.geo;
     cp_async_wait_all();
@@ -162,31 +192,62 @@ k_wpt_rev_tile(const __grid_constant__ Taps taps, const __grid_constant__ WptRev
     for (int k = m; k >= 1; --k) {
       double t[2 * kRS];
       int par = 0, g = 0;
-      bool has = false;
       const int Fk = k == 1 ? 0 : Fx;                          // F_1 == 0: no extension at the output level
       const int cap_in = capB >> k, cap_out = capB >> (k - 1);
       const int g0k = k == m ? (ru8 >> 3) : ((2 * Fx - Fk) >> 3);
       const int gl = Fk >> lgRS;
+      // tail warp: Fk / 2 two-slot steps per parent, up to kTailSteps per lane (a deep pass has 2^(k-1) parents:
+      // 128 steps at k = 6); their results share the registers of a main step
+      constexpr int kTailSteps = (2 * kRS) / 4;
+      const int per_par = Fk >> 1, items = per_par << (k - 1);
       if (tid < nmain) {
         const int lg_gpp = lgT - k - lgRS;
         par = tid >> lg_gpp;
         g = gl + (tid & ((1 << lg_gpp) - 1));
         main_step(cur + (2 * par) * cap_in, cap_in, (kRS == 8 ? g0k : 2 * g0k) + g, t);
       } else if (k > 1) {
-        const int per_par = Fk >> 1;
-        g = tid - nmain;
-        has = g < (per_par << (k - 1));
-        if (has) {
-          while (g >= per_par) { g -= per_par; ++par; }
-          double t4[4];
-          tail_step(cur + (2 * par) * cap_in, cap_in, 4 * g0k + g, t4);
-          t[0] = t4[0]; t[1] = t4[1]; t[2] = t4[2]; t[3] = t4[3];
+#pragma unroll
+        for (int i = 0; i < kTailSteps; ++i) {
+          const int it = tid - nmain + 32 * i;
+          if (it < items) {
+            const int tp = it / per_par, tg = it - tp * per_par;
+            double t4[4];
+            tail_step(cur + (2 * tp) * cap_in, cap_in, 4 * g0k + tg, t4);
+            t[4 * i] = t4[0]; t[4 * i + 1] = t4[1]; t[4 * i + 2] = t4[2]; t[4 * i + 3] = t4[3];
+          }
+        }
+      }
+      // Output level with a TMA store (a.tma_out): once every window of level 1 has been read the buffer is free;
+      // thread g writes its 16 samples as row g of a dense [T / 16][16] image, chunk e at e ^ (g & 7) (conflict-free,
+      // registers in program order), and one thread hands the image to the copy engine - no 32 x 32-byte STG per
+      // warp and instruction, no store drain before the CTA retires (profiles/r02_lsu_bound.md, ablation table).
+      const bool tma_out = (k == 1) && a.tma_out && kRS == 8;
+      if (k > 1 || tma_out) __syncthreads();
+      if (tid < nmain) {
+        if (tma_out) {
+          double2* row = smem2 + 8 * g;  // k == 1: one parent, gl == 0, g == tid
+          const int x = g & 7;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) row[e ^ x] = make_double2(t[2 * e], t[2 * e + 1]);
+        } else {
+          main_store(k, nxt + par * cap_out, g, gl, t);
+        }
+      } else if (k > 1) {
+#pragma unroll
+        for (int i = 0; i < kTailSteps; ++i) {
+          const int it = tid - nmain + 32 * i;
+          if (it < items) {
+            const int tp = it / per_par, tg = it - tp * per_par;
+            tail_store(nxt + tp * cap_out, tg, &t[4 * i]);
+          }
         }
       }
       if (k > 1) __syncthreads();
-      if (tid < nmain) main_store(k, nxt + par * cap_out, g, gl, t);
-      else if (has) tail_store(nxt + par * cap_out, g, t);
-      if (k > 1) __syncthreads();
+      else if (tma_out) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the TMA
+        __syncthreads();
+        if (tid == 0) tma_store_tile(&tmapOut, smem2, 0, int((line * h0 + t0) >> 4));
+      }
     }
   } else {
     for (int k = m; k >= 1; --k) {
@@ -350,6 +411,35 @@ int wpt_rev_tile_levels(int L, int T, int want, size_t smem_limit) {
   return m;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFnW)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFnW encode_tiled_w() {
+  static EncodeTiledFnW fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFnW>(p);
+  }();
+  return fn;
+}
+// the output lines, dense, as a [rows][16 doubles] matrix; box {16, box_rows}; 128-byte swizzle on the shared side
+static bool make_out_tmap(CUtensorMap* map, const double* base, int64_t rows, int box_rows) {
+  EncodeTiledFnW enc = encode_tiled_w();
+  if (!enc || (reinterpret_cast<uintptr_t>(base) & 127) || rows < 1 || rows >= (int64_t(1) << 31) || box_rows < 1 || box_rows > 256)
+    return false;
+  const cuuint64_t dims[2] = {16, cuuint64_t(rows)};
+  const cuuint64_t strides[1] = {16 * sizeof(double)};
+  const cuuint32_t box[2] = {16, cuuint32_t(box_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int L>
 static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, WptRevArgs a, bool resident) {
   size_t smem;
@@ -364,8 +454,13 @@ static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, WptRevArgs a, bool r
     a.stage_left = a.F[a.m] + a.ru8;
     a.stage_len2 = a.len[a.m] / 2;
     a.cap_m = a.cap[a.m];
-    for (int k = 2; k <= a.m; ++k)  // tail steps of a level: one per lane of the tail warp
-      if (((a.F[k] >> 1) << (k - 1)) > 32) inplace = false;
+    for (int k = 2; k <= a.m; ++k)  // tail steps of a level: up to 4 (kRS = 8) / 2 (kRS = 4) per lane of the tail warp
+      if (((a.F[k] >> 1) << (k - 1)) > 32 * (ctx->wpt_rs == 4 ? 2 : 4)) inplace = false;
+    a.stage_lg_lpn = -1;
+    if (a.stage_len2 * 2 <= ctx->wpt_threads) {  // short packets: several per staging round
+      a.stage_lg_lpn = 0;
+      while ((1 << a.stage_lg_lpn) < a.stage_len2) ++a.stage_lg_lpn;
+    }
     if (inplace) smem /= 2;
     a.tiles_per_line = a.h0 / a.T;
     a.rot = (JWC_WPT_TAIL_WARP && ctx->rot_warps) ? 1 : 0;
@@ -382,17 +477,34 @@ static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, WptRevArgs a, bool r
     grid = (a.lines + a.G - 1) / a.G;
   }
   if (grid > 0x7fffffff) return cudaErrorInvalidConfiguration;
-  auto kern = resident ? (ctx->wpt_rs == 4 ? k_wpt_rev_res<L, 4> : k_wpt_rev_res<L, 8>)
-                       : inplace ? (ctx->wpt_rs == 4 ? k_wpt_rev_tile<L, 4, true> : k_wpt_rev_tile<L, 8, true>)
-                                 : (ctx->wpt_rs == 4 ? k_wpt_rev_tile<L, 4, false> : k_wpt_rev_tile<L, 8, false>);
-  if (!resident) smem += size_t(ctx->xsmem) << 10;
+  if (resident) {
+    auto rk = ctx->wpt_rs == 4 ? k_wpt_rev_res<L, 4> : k_wpt_rev_res<L, 8>;
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+      if (e != cudaSuccess) return e;
+    }
+    prof_begin(ctx, "k_wpt_rev:resident", double(a.lines) * a.h0, a.m);
+    rk<<<int(grid), ctx->wpt_threads, smem, ctx->stream>>>(taps, a);
+    prof_end(ctx);
+    ctx->launches++;
+    return cudaGetLastError();
+  }
+  auto kern = inplace ? (ctx->wpt_rs == 4 ? k_wpt_rev_tile<L, 4, true> : k_wpt_rev_tile<L, 8, true>)
+                      : (ctx->wpt_rs == 4 ? k_wpt_rev_tile<L, 4, false> : k_wpt_rev_tile<L, 8, false>);
+  CUtensorMap tmapOut;
+  memset(&tmapOut, 0, sizeof tmapOut);
+  a.tma_out = 0;
+  if (inplace && ctx->wpt_tma_store && ctx->wpt_rs != 4 && a.dst_os == a.h0 && a.T >= 256 && a.T <= 4096 &&
+      smem >= size_t(a.T) * sizeof(double) && make_out_tmap(&tmapOut, a.dst, a.lines * (a.h0 / 16), a.T / 16))
+    a.tma_out = 1;
+  smem += size_t(ctx->xsmem) << 10;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
   }
   if (ctx->carve) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  prof_begin(ctx, resident ? "k_wpt_rev:resident" : "k_wpt_rev:tile", double(a.lines) * a.h0, a.m);
-  kern<<<int(grid), ctx->wpt_threads, smem, ctx->stream>>>(taps, a);
+  prof_begin(ctx, "k_wpt_rev:tile", double(a.lines) * a.h0, a.m);
+  kern<<<int(grid), ctx->wpt_threads, smem, ctx->stream>>>(taps, a, tmapOut);
   prof_end(ctx);
   ctx->launches++;
   return cudaGetLastError();
