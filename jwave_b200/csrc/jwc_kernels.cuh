@@ -100,6 +100,7 @@ struct WptFwdArgs {
   // filled in by the launcher
   int tiles_per_line, lg_tpl, lg_T, buf_cap, rot;
   int stagger_ns, stagger_ctas, stagger_div;  // first-wave stagger (A/B switch, jwc_fused.cuh)
+  int tma_out;                          // tile mode, in place: the leaf segments leave through TMA stores
   int cap[kMaxFuse + 1];                // tile mode: per-node capacity (double2) of level k
 };
 int wpt_tile_levels(int L, int T, int want, size_t smem_limit, int R);

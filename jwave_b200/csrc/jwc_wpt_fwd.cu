@@ -17,6 +17,10 @@
 //                                  line + j * (h >> m) + tile * (T >> m).
 //   resident mode  (h <= res_cap): one CTA = G whole lines, wrap by index mask; nodes shorter than
 //                                  4 samples take a scalar path with true modular indexing.
+#include <cuda.h>
+
+#include <cstring>
+
 #include "jwc_fused.cuh"
 #include "jwc_kernels.cuh"
 
@@ -55,10 +59,20 @@ template <int R> __device__ __forceinline__ void lscalar_store(double2* buf, int
 // level) are a separate short step, two outputs per lane, instead of one more nearly empty R-wide step
 // for every warp; JWC_WPT_TAIL_WARP selects who runs it: a dedicated extra warp (1) or one of the
 // main warps, rotating with the CTA and the level so that no SM sub-partition collects all of it (0).
+// TMA store of one finished leaf-packet segment (cp.async.bulk.tensor, SASS UTMASTG): box {16 doubles, (T >> m) / 16
+// rows} of the output seen as a [rows][16] matrix, from a dense, 128-byte-swizzled shared-memory image (jwc_wpt_rev.cu).
+__device__ __forceinline__ void tma_store_box_w(const void* tmap, const void* smem_src, int x, int y) {
+  const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_src));
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap), "r"(x), "r"(y), "r"(s)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 template <int L, int R, bool INPLACE>
 __global__ void JWC_WPT_TILE_BOUNDS
-k_wpt_fwd_tile(const __grid_constant__ Taps taps, const __grid_constant__ WptFwdArgs a) {
-  extern __shared__ double2 smem2[];
+k_wpt_fwd_tile(const __grid_constant__ Taps taps, const __grid_constant__ WptFwdArgs a, const __grid_constant__ CUtensorMap tmapOut) {
+  extern __shared__ __align__(1024) double2 smem2[];
   constexpr int lgR = (R == 8) ? 3 : 2;
   static_assert(R == 8 || R == 4, "R is 4 or 8");
   const int tid = rotated_tid(a.rot), nthr = blockDim.x, nmain = nthr - 32 * JWC_WPT_TAIL_WARP;
@@ -118,6 +132,31 @@ k_wpt_fwd_tile(const __grid_constant__ Taps taps, const __grid_constant__ WptFwd
         }
       }
       if (last) {
+        if (a.tma_out && R == 8) {
+          // The 2^m leaf segments of the tile leave through TMA stores: the buffer is free once every window of the
+          // last level has been read; the segment of leaf j is a dense [(T >> m) / 16][16] image at 16 (T >> m) bytes x j,
+          // thread (node, g) owns half a row of leaves 2 node and 2 node + 1, chunks XOR-swizzled by the row number
+          // (conflict-free); lanes 0 .. 2^m - 1 of warp 0 each hand one segment to the copy engine.
+          __syncthreads();
+          const int seg2 = (T >> m) >> 1;  // double2 per leaf segment
+          if (tid < nmain) {
+            const int row = g >> 1, x = row & 7, c0 = 4 * (g & 1);
+            double2* ia = smem2 + (2 * node) * seg2 + 8 * row;
+            double2* id = ia + seg2;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              ia[(c0 + e) ^ x] = make_double2(lo[2 * e], lo[2 * e + 1]);
+              id[(c0 + e) ^ x] = make_double2(hi[2 * e], hi[2 * e + 1]);
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncthreads();
+          if (tid < (1 << m)) {
+            const int64_t leaf = h >> m;
+            tma_store_box_w(&tmapOut, smem2 + tid * seg2, 0, int((line * a.dst_os + tid * leaf + (base >> m)) >> 4));
+          }
+          break;
+        }
         if (tid < nmain) {
           const int leaf = h >> m;
           double* pa = a.dst + line * a.dst_os + int64_t(2 * node) * leaf + (base >> m) + R * g;
@@ -316,6 +355,35 @@ int wpt_tile_levels(int L, int T, int want, size_t smem_limit, int R) {
   return m;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFnF)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFnF encode_tiled_f() {
+  static EncodeTiledFnF fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFnF>(p);
+  }();
+  return fn;
+}
+// the output lines, dense, as a [rows][16 doubles] matrix; box {16, box_rows}; 128-byte swizzle on the shared side
+static bool make_out_tmap_f(CUtensorMap* map, const double* base, int64_t rows, int box_rows) {
+  EncodeTiledFnF enc = encode_tiled_f();
+  if (!enc || (reinterpret_cast<uintptr_t>(base) & 127) || rows < 1 || rows >= (int64_t(1) << 31) || box_rows < 1 || box_rows > 256)
+    return false;
+  const cuuint64_t dims[2] = {16, cuuint64_t(rows)};
+  const cuuint64_t strides[1] = {16 * sizeof(double)};
+  const cuuint32_t box[2] = {16, cuuint32_t(box_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int L, int R>
 static cudaError_t launch_LR(jwc_ctx* ctx, const Taps& taps, WptFwdArgs a, bool resident) {
   size_t smem;
@@ -346,15 +414,35 @@ static cudaError_t launch_LR(jwc_ctx* ctx, const Taps& taps, WptFwdArgs a, bool 
     grid = (a.lines + a.G - 1) / a.G;
   }
   if (grid > 0x7fffffff) return cudaErrorInvalidConfiguration;
-  auto kern = resident ? k_wpt_fwd_res<L, R> : inplace ? k_wpt_fwd_tile<L, R, true> : k_wpt_fwd_tile<L, R, false>;
   if (!resident) smem += size_t(ctx->xsmem) << 10;
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    if (e != cudaSuccess) return e;
+  {
+    const void* kern = resident ? reinterpret_cast<const void*>(k_wpt_fwd_res<L, R>)
+                                : inplace ? reinterpret_cast<const void*>(k_wpt_fwd_tile<L, R, true>)
+                                          : reinterpret_cast<const void*>(k_wpt_fwd_tile<L, R, false>);
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+      if (e != cudaSuccess) return e;
+    }
+    if (ctx->carve) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   }
-  if (ctx->carve) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  prof_begin(ctx, resident ? "k_wpt_fwd:resident" : "k_wpt_fwd:tile", double(a.lines) * a.h, a.m);
-  kern<<<int(grid), nthr, smem, ctx->stream>>>(taps, a);
+  if (resident) {
+    prof_begin(ctx, "k_wpt_fwd:resident", double(a.lines) * a.h, a.m);
+    k_wpt_fwd_res<L, R><<<int(grid), nthr, smem, ctx->stream>>>(taps, a);
+    prof_end(ctx);
+    ctx->launches++;
+    return cudaGetLastError();
+  }
+  CUtensorMap tmapOut;
+  memset(&tmapOut, 0, sizeof tmapOut);
+  a.tma_out = 0;
+  const int seg = a.T >> a.m;  // samples per leaf segment of a tile
+  if (inplace && R == 8 && ctx->wpt_tma_store_fwd && a.dst_os == a.h && seg % 128 == 0 && seg / 16 <= 256 && (a.h >> a.m) % 16 == 0 &&
+      (1 << a.m) <= 32 && smem >= size_t(a.T) * sizeof(double) + (size_t(ctx->xsmem) << 10) &&
+      make_out_tmap_f(&tmapOut, a.dst, a.lines * (a.h / 16), seg / 16))
+    a.tma_out = 1;
+  prof_begin(ctx, "k_wpt_fwd:tile", double(a.lines) * a.h, a.m);
+  if (inplace) k_wpt_fwd_tile<L, R, true><<<int(grid), nthr, smem, ctx->stream>>>(taps, a, tmapOut);
+  else k_wpt_fwd_tile<L, R, false><<<int(grid), nthr, smem, ctx->stream>>>(taps, a, tmapOut);
   prof_end(ctx);
   ctx->launches++;
   return cudaGetLastError();

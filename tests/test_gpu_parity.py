@@ -456,3 +456,27 @@ def test_two_tap_shuffle_kernel(monkeypatch, cls):
             assert np.array_equal(got, off.forwardBatch(x, level)), (n, level)
             back = np.stack([co.transform_1d(co.FWT, co.REVERSE, cls, want[b], level) for b in range(batch)])
             close(on.reverseBatch(want, level), back, np.abs(want).max())
+
+
+@pytest.mark.parametrize("cls", ["Symlet8", "Daubechies20", "Haar1"])
+def test_packet_transform_tma_stores(monkeypatch, cls):
+    """The WPT tile kernels hand finished tiles to the copy engine (cp.async.bulk.tensor stores from a 128-byte-swizzled
+    shared-memory image, jwc_wpt_rev.cu / jwc_wpt_fwd.cu).  Reverse: on by default; forward: JWC_TUNE
+    wpt_tma_store_fwd=1.  Both must be bit-identical to the register stores (wpt_tma_store=0) and match the oracle, on
+    widths with one and with several tiles per line and passes of 3, 2 and 1 levels; wpt_rev_m=6 runs the reverse as
+    ONE pass of 6 levels (several tail steps per lane, short-packet staging)."""
+    w = jw.WaveletBuilder.create(cls)
+    ctxs = {t: jw.CudaWaveletPacketTransform(w, context=_tuned_context(monkeypatch, t))
+            for t in ("", "wpt_tma_store=0", "wpt_tma_store_fwd=1", "wpt_rev_m=6")}
+    for n, batch, level in ((1 << 16, 3, 6), (1 << 13, 5, 5), (2048, 9, 3), (4096, 2, 1), (1 << 14, 2, 14)):
+        x = rng_signal(n + level, batch, n)
+        want = np.stack([co.transform_1d(co.WPT, co.FORWARD, cls, x[b], level) for b in range(batch)])
+        back = np.stack([co.transform_1d(co.WPT, co.REVERSE, cls, want[b], level) for b in range(batch)])
+        f0 = ctxs["wpt_tma_store=0"].forwardBatch(x, level)
+        r0 = ctxs["wpt_tma_store=0"].reverseBatch(want, level)
+        close(f0, want, np.abs(x).max())
+        close(r0, back, np.abs(want).max())
+        for t in ("", "wpt_tma_store_fwd=1"):
+            assert np.array_equal(ctxs[t].forwardBatch(x, level), f0), (t, n, level)
+            assert np.array_equal(ctxs[t].reverseBatch(want, level), r0), (t, n, level)
+        close(ctxs["wpt_rev_m=6"].reverseBatch(want, level), back, np.abs(want).max())
