@@ -150,6 +150,9 @@ k_fwt_rev(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevArgs 
             store_group<kRS>(Y, g, t);
           } else {
             double* y = (a.rm.mode ? remote_line(a.rm, line) : a.dst + line * a.dst_os) + t0 + 2 * kRS * g;
+#ifdef JWC_ABLATE_STG  // timing experiment only (tools/build_variant.sh): the kernel without its output stores
+            if (t[0] == 123.456)
+#endif
 #pragma unroll
             for (int e = 0; e < kRS / 2; ++e) st_global_v4(y + 4 * e, t[4 * e], t[4 * e + 1], t[4 * e + 2], t[4 * e + 3]);
             static_assert(kRS >= 2, "a group stores at least 4 samples");
