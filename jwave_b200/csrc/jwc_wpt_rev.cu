@@ -70,13 +70,26 @@ __device__ __forceinline__ void wrev_step(const Taps& taps, A2 a2, D2 d2, double
 // step, two slots per lane, run by a dedicated extra warp (JWC_WPT_TAIL_WARP = 1) or by one of the main
 // warps, rotating with the CTA and the level (0); see jwc_wpt_fwd.cu.
 //
-// Shared-memory layout of a node: double2 k at k + (k >> 3), one pad slot per 8 (rl).  The lanes of an LDS.128 phase
-// read windows 4 slots apart (8 g', ..): positions floor(9 (4 g' + c) / 8) hit the 8 bank groups 0,4,1,5,2,6,3,7; the
-// lanes of an STS.128 phase store runs of 8 slots, 9 positions apart: also 8 distinct groups.  Both are conflict-free
-// WITHOUT the rotated store order the stride-4 padding (pad2) needed - that cost 32 FSEL per level - and every 4-slot
-// block is contiguous, so a window is two block pointers plus compile-time offsets.
+// Shared-memory layout of a node: double2 k at k + (k >> 3), one pad slot per 8 (rl).  A thread's window is two
+// 4-slot blocks, G and G - 1; the lanes of an LDS.128 phase read blocks 4 slots apart, positions floor(9 j / 2): the 8
+// bank groups 0,4,1,5,2,6,3,7 when the phase starts at an even block, one colliding lane pair (2-way) when it starts at
+// an odd one - so one of the two blocks pays (ncu: 6 of the 16 window loads at 2 wavefront passes).  The lanes of an
+// STS.128 phase store runs of 8 slots, 9 positions apart: 8 distinct groups, no rotated store order.  The alternative
+// (JWC_WPT_REV_PAD4=1: one pad per 4, stride 5 - every load phase conflict-free, stores rotated with 32 FSEL per level)
+// measures the same or 1-2 % slower (profiles/r02_lsu_bound.md); every 4-slot block is contiguous in both, so a
+// window is two block pointers plus compile-time offsets.
+#ifndef JWC_WPT_REV_PAD4
+#define JWC_WPT_REV_PAD4 0
+#endif
+#if JWC_WPT_REV_PAD4  // A/B: one pad slot per 4 (window loads conflict-free at any phase, rotated stores)
+__device__ __forceinline__ int rl(int k2) { return k2 + (k2 >> 2); }
+__host__ __device__ constexpr int rl_size(int n2) { return n2 + (n2 >> 2) + 2; }
+constexpr int kTwoBlocks = 10;
+#else
 __device__ __forceinline__ int rl(int k2) { return k2 + (k2 >> 3); }
 __host__ __device__ constexpr int rl_size(int n2) { return n2 + (n2 >> 3) + 2; }
+constexpr int kTwoBlocks = 9;
+#endif
 
 // TMA store of the finished tile (cp.async.bulk.tensor, SASS UTMASTG): box {16 doubles, T / 16 rows} of the output seen
 // as a [rows][16] matrix, read from a dense shared-memory image whose 16-byte chunks are XOR-swizzled by the row number
@@ -146,9 +159,9 @@ k_wpt_rev_tile(const __grid_constant__ Taps taps, const __grid_constant__ WptRev
       // slot 4G + 3 - w sits in 4-block G - (w >> 2).  Blocks G, G - 2, .. are 9 positions apart from o1 = rl(4G),
       // blocks G - 1, G - 3, .. from o0 = rl(4 (G - 1)): two run-time offsets, everything else folds (block G - 1 is
       // never read for L = 2, whose window is 4 slots).
-      const int o1 = 4 * G + (G >> 1), o0 = 4 * (G - 1) + ((G - 1) >> 1);
+      const int o1 = rl(4 * G), o0 = rl(4 * (G - 1));
       auto at = [&](const double2* X, int w) {
-        const int blk = w >> 2, e = 3 - (w & 3) - 9 * (blk >> 1);
+        const int blk = w >> 2, e = 3 - (w & 3) - kTwoBlocks * (blk >> 1);
         return (blk & 1) ? X[o0 + e] : X[o1 + e];
       };
       wrev_step<L, 8>(taps, [&](int w) { return at(A, w); }, [&](int w) { return at(D, w); }, t);
@@ -160,8 +173,27 @@ k_wpt_rev_tile(const __grid_constant__ Taps taps, const __grid_constant__ WptRev
   auto main_store = [&](int k, double2* Yn, int g, int gl, const double (&t)[2 * kRS]) {
     if (k > 1) {
       double2* Y = Yn + rl(kRS * g);  // kRS = 8: 9 g; kRS = 4: runs of 4 inside one 8-block
+#if JWC_WPT_REV_PAD4
+      if constexpr (kRS == 8) {
+        // lanes 10 slots apart: groups g and g + 4 share a bank group; lanes with bit 2 of g set store their upper
+        // four slots first (slot e ^ 4 sits 5 padded slots from slot e)
+        const bool rot = (g >> 2) & 1;
+        double2* Ylo = Y + (rot ? 5 : 0);
+        double2* Yhi = Y - (rot ? 5 : 0);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          Ylo[e] = make_double2(rot ? t[2 * e + 8] : t[2 * e], rot ? t[2 * e + 9] : t[2 * e + 1]);
+#pragma unroll
+        for (int e = 4; e < 8; ++e)
+          Yhi[e + 1] = make_double2(rot ? t[2 * e - 8] : t[2 * e], rot ? t[2 * e - 7] : t[2 * e + 1]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < kRS; ++e) Y[e] = make_double2(t[2 * e], t[2 * e + 1]);
+      }
+#else
 #pragma unroll
       for (int e = 0; e < kRS; ++e) Y[e] = make_double2(t[2 * e], t[2 * e + 1]);
+#endif
     } else {
       double* y = a.dst + line * a.dst_os + t0 + 2 * kRS * (g - gl);
 #pragma unroll
