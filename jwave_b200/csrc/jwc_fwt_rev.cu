@@ -117,6 +117,7 @@ k_fwt_rev(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevArgs 
       const int O = (k == m) ? ((t0 >> k) - a.F[k] - a.ru8) : 2 * ((t0 >> (k + 1)) - a.F[k + 1]);
       double2* D = smem2 + a.offD[k];
       const double* dk = lineD + wk;
+#ifndef JWC_ABLATE_LD  // (timing experiments only: the kernel without its staging loads / FMA steps / output stores)
       for (int j2 = tid; j2 < a.len[k] / 2; j2 += nthr)
         cp_async16(&D[lay(j2)], dk + ((O + 2 * j2) & (wk - 1)));
       if (k == m) {
@@ -125,6 +126,7 @@ k_fwt_rev(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevArgs 
         for (int j2 = tid; j2 < a.len[k] / 2; j2 += nthr)
           cp_async16(&A[lay(j2)], am + ((O + 2 * j2) & (wk - 1)));
       }
+#endif
       cp_async_commit();
     }
 
@@ -145,7 +147,12 @@ k_fwt_rev(const __grid_constant__ Taps taps, const __grid_constant__ FwtRevArgs 
         for (int g = gl + tid; g < groups; g += nmain) {
           double t[2 * kRS];
           const int c = 4 * g0 + (kRS / 2) * g + kRS / 2 - 1;
+#ifdef JWC_ABLATE_FMA
+#pragma unroll
+          for (int e = 0; e < 2 * kRS; ++e) t[e] = A[lay(c)].x;
+#else
           rev_step<L, kRS>(taps, [&](int w) { return A[lay(c - w)]; }, [&](int w) { return D[lay(c - w)]; }, t);
+#endif
           if (k > 1) {
             store_group<kRS>(Y, g, t);
           } else {
