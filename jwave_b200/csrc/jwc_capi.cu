@@ -115,6 +115,7 @@ extern "C" int jwc_create(jwc_ctx** out, int device) {
         {"carve", &ctx->carve, false, 0, 1},                     {"xsmem", &ctx->xsmem, false, 0, 200},
         {"stagger", &ctx->stagger, false, 0, 100000},              {"res_kb", &ctx->res_kb, false, 4, 200},
         {"wpt_transpose", &ctx->wpt_transpose, false, 0, 1},  {"res_split", &ctx->res_split, true, 0, 4096},
+        {"pf", &ctx->pf, false, 0, 1 << 20},
         {"wpt_tma_store", &ctx->wpt_tma_store, false, 0, 1},  {"wpt_tma_store_fwd", &ctx->wpt_tma_store_fwd, false, 0, 1},
         {"wpt_rev_m", &ctx->wpt_rev_m, false, 0, 12},
     };

@@ -137,6 +137,7 @@ struct jwc_ctx {
   int wpt_rev_m = 0;  // WPT reverse: levels per tile pass (0 = wpt_m); the reverse's left extension does not grow with depth
   int wpt_tma_store = 1;  // WPT reverse tile kernel: finished tiles leave through cp.async.bulk.tensor stores
   int wpt_tma_store_fwd = 0;  // the same for the forward kernel's 2^m leaf segments (measured neutral: its 64-byte runs per lane were not the limit)
+  int pf = 0;         // WPT tile kernels: L2 prefetch (cp.async.bulk.prefetch.L2) of the tile `pf` CTAs ahead; 0 = off
   int res_split = 0;  // resident FWT forward: split the resident work at this width (0 = one launch), jwc_plan.cu
   int res_kb = 48;    // resident kernels: shared-memory budget per CTA (KB) that sets the lines per CTA
   int stagger = 0;    // WPT tile kernels: first-wave stagger in ns per resident-CTA slot (jwc_fused.cuh)

@@ -100,6 +100,7 @@ struct WptFwdArgs {
   // filled in by the launcher
   int tiles_per_line, lg_tpl, lg_T, buf_cap, rot;
   int stagger_ns, stagger_ctas, stagger_div;  // first-wave stagger (A/B switch, jwc_fused.cuh)
+  int pf_dist;                          // L2 prefetch distance in CTAs (0 = off)
   int tma_out;                          // tile mode, in place: the leaf segments leave through TMA stores
   int cap[kMaxFuse + 1];                // tile mode: per-node capacity (double2) of level k
 };
@@ -115,6 +116,7 @@ struct WptRevArgs {
   // filled in by the launcher
   int tiles_per_line, lg_tpl, lg_T, ru8, buf_cap, rot;
   int stagger_ns, stagger_ctas, stagger_div;  // first-wave stagger (A/B switch, jwc_fused.cuh)
+  int pf_dist;                          // L2 prefetch distance in CTAs (0 = off)
   int stage_left, stage_len2, cap_m;    // tile mode, staging: F[m] + ru8, len[m] / 2, cap[m]
   int stage_lg_lpn;                     // staging: log2 threads per packet when packets are short, else -1
   int tma_out;                          // tile mode, in place: the finished tile leaves through a TMA store

@@ -96,6 +96,14 @@ k_wpt_fwd_tile(const __grid_constant__ Taps taps, const __grid_constant__ WptFwd
     sp -= h;
 #pragma unroll 1
     for (; k2 < n2; k2 += nthr, sp += 2 * nthr, dp += step) cp_async16(dp, sp);
+    // L2 prefetch of the tile a CTA `pf_dist` launches later will stage (one instruction, no registers, no wait)
+    if (a.pf_dist > 0 && tid == 0) {
+      const int64_t t2 = int64_t(blockIdx.x) + a.pf_dist;
+      if (t2 < (a.lines << a.lg_tpl)) {
+        const double* p2 = a.src + (t2 >> a.lg_tpl) * a.src_os + (int(t2) & (a.tiles_per_line - 1)) * T;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p2), "r"(T * 8) : "memory");
+      }
+    }
     cp_async_wait_all();
     __syncthreads();
   }
@@ -403,6 +411,7 @@ static cudaError_t launch_LR(jwc_ctx* ctx, const Taps& taps, WptFwdArgs a, bool 
     a.tiles_per_line = a.h / a.T;
     a.rot = (JWC_WPT_TAIL_WARP && ctx->rot_warps) ? 1 : 0;
     a.stagger_ns = ctx->stagger;
+    a.pf_dist = ctx->pf;
     a.stagger_div = ctx->sm_count;
     a.stagger_ctas = ctx->sm_count * 8;
     a.lg_tpl = ilog2(a.tiles_per_line);

@@ -148,6 +148,15 @@ k_wpt_rev_tile(const __grid_constant__ Taps taps, const __grid_constant__ WptRev
       }
     }
     if (tid == 0) s_geo = a.geo;
+    // L2 prefetch of the leaf-packet segments a CTA `pf_dist` launches later will stage (one instruction per packet)
+    if (a.pf_dist > 0 && tid < nn) {
+      const int64_t t2 = int64_t(blockIdx.x) + a.pf_dist;
+      if (t2 < (a.lines << a.lg_tpl)) {
+        const int O2 = (((int(t2) & (a.tiles_per_line - 1)) * T) >> m) & ~15;  // the kept slots, 128-byte aligned
+        const double* p2 = a.src + (t2 >> a.lg_tpl) * a.src_os + int64_t(tid) * wm + O2;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p2), "r"((T >> m) * 8) : "memory");
+      }
+    }
     cp_async_wait_all();
     __syncthreads();
   }
@@ -497,6 +506,7 @@ static cudaError_t launch_L(jwc_ctx* ctx, const Taps& taps, WptRevArgs a, bool r
     a.tiles_per_line = a.h0 / a.T;
     a.rot = (JWC_WPT_TAIL_WARP && ctx->rot_warps) ? 1 : 0;
     a.stagger_ns = ctx->stagger;
+    a.pf_dist = ctx->pf;
     a.stagger_div = ctx->sm_count;
     a.stagger_ctas = ctx->sm_count * 8;
     auto ilog2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
