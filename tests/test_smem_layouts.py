@@ -4,7 +4,7 @@ STS.128 pattern the tile kernels issue is enumerated lane by lane and must be fr
 A 128-bit shared access is served per quarter-warp (8 lanes x 16 B = one 128-byte wavefront); two lanes of a
 quarter conflict when their double2 slots differ but fall into the same 16-byte bank group (slot mod 8).
 The index formulas restate jwave_b200/csrc: pad2 / padr (jwc_fused.cuh, jwc_wpt_fwd.cu), lay and
-store_group (jwc_fwt_rev.cu), the rotated stores of jwc_wpt_rev.cu."""
+store_group (jwc_fwt_rev.cu), rl and the TMA-store images of jwc_wpt_rev.cu / jwc_wpt_fwd.cu."""
 import itertools
 
 
@@ -72,7 +72,8 @@ def test_wpt_layouts():
         assert wavefronts([9 * g + q + q // 8 for g in range(32)]) == 4
     for e in range(4):
         assert wavefronts([4 * g + (g >> 1) + e for g in range(32)]) == 4
-    # k_wpt_rev_tile, kRS = 8: windows at stride 5 (pad2 of 4 g' + 3 - w), rotated stores at stride 10
+    # k_wpt_rev_tile, kRS = 8, -DJWC_WPT_REV_PAD4=1 (the A/B alternative): windows at stride 5 (pad2 of 4 g' + 3 - w),
+    # rotated stores at stride 10
     for w in range(8):
         assert wavefronts([5 * g + (3 - w) + ((3 - w) >> 2) + 64 for g in range(32)]) == 4
     for e in range(8):
@@ -84,3 +85,25 @@ def test_wpt_layouts():
             ee = e ^ 4 if rot else e
             rotated.append(10 * g + ee + (ee >> 2))
         assert wavefronts(rotated) == 4
+
+
+def rl(k):
+    return k + (k >> 3)
+
+
+def test_wpt_reverse_pad_per_8_and_tma_images():
+    """k_wpt_rev_tile as shipped: one pad slot per 8 (rl).  A thread's window is the 4-slot blocks G and G - 1 with
+    G = g0 + group number, g0 + gl == 2 at every level of the C3 geometry: the loads of block G (phases start at an
+    even block) are conflict-free, the loads of block G - 1 collide in one lane pair per phase (2 passes - what the ncu
+    source page shows for 6 of the 16 window loads); the 8-slot result runs are conflict-free without a rotated order."""
+    for w in range(4):
+        assert wavefronts([rl(4 * (2 + g)) + 3 - w for g in range(32)]) == 4
+        assert wavefronts([rl(4 * (1 + g)) + 3 - w for g in range(32)]) == 8
+    for e in range(8):
+        assert wavefronts([rl(8 * g) + e for g in range(32)]) == 4
+    # images of the TMA stores (SWIZZLE_128B: 16-byte chunk c of 128-byte row r sits at c ^ (r & 7)):
+    # reverse - thread g owns row g; forward - thread g owns half of row g >> 1 of two leaf segments
+    for e in range(8):
+        assert wavefronts([8 * g + (e ^ (g & 7)) for g in range(32)]) == 4
+    for e in range(4):
+        assert wavefronts([8 * (g >> 1) + ((4 * (g & 1) + e) ^ ((g >> 1) & 7)) for g in range(32)]) == 4
