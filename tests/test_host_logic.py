@@ -77,3 +77,25 @@ def test_transform_builder_rejects_unknown_names():
         jw.TransformBuilder.create("Discrete Fourier Transform", "Haar")
     with pytest.raises(jw.JWaveFailure):
         jw.TransformBuilder.create("Fast Wavelet Transform", "no such wavelet")
+
+
+def test_qbench_tap_tables_are_the_library_taps():
+    """tools/qbench_taps.h (the native A/B driver's filter tables, hex float literals) must be bit-identical to the
+    four getter arrays of the Python wavelets it was generated from."""
+    import os
+    import re
+    import jwave_b200 as jw
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "qbench_taps.h")
+    text = open(path).read()
+    entries = re.findall(r'\{"(\w+)", (\d+), \{(.*?)\}\},', text, flags=re.S)
+    assert len(entries) >= 5
+    for name, L, body in entries:
+        w = jw.WaveletBuilder.create(name)
+        rows = re.findall(r"\{([^{}]*)\}", body)
+        want = (w.getScalingDeComposition(), w.getWaveletDeComposition(),
+                w.getScalingReConstruction(), w.getWaveletReConstruction())
+        assert len(rows) == 4
+        for row, arr in zip(rows, want):
+            got = [float.fromhex(t.strip()) for t in row.split(",") if t.strip()]
+            assert len(got) == int(L) == len(arr)
+            assert all(a == float(b) for a, b in zip(got, arr)), name
